@@ -1,0 +1,358 @@
+"""Diagnostic probe: runs every libvitseg kernel against a plain PyTorch fp32 computation on the GPU and prints
+error statistics without stopping at the first failure.  Development aid for gpurun sessions; the pass/fail
+versions of these checks live in tests/test_kernels_gpu.py.
+
+usage: python tools/kernel_probe.py [gemm] [ln] [attn] [head] [loss] ..."""
+import os
+import sys
+import traceback
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from visiontransformer_b200 import kernels as K  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+RESULTS = []
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def report(name, err, tol):
+    ok = err <= tol and err == err
+    RESULTS.append((name, err, tol, ok))
+    print(f"{'PASS' if ok else 'FAIL'} {name:58s} err={err:.3e} tol={tol:.1e}", flush=True)
+
+
+def run(name, fn):
+    try:
+        fn()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        RESULTS.append((name, float("nan"), 0, False))
+        print(f"FAIL {name}: EXCEPTION {type(e).__name__}: {e}", flush=True)
+        traceback.print_exc()
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------------------------
+def probe_gemm():
+    def case(M, N, Kd, a_mn, b_mn, **kw):
+        def f():
+            a = bf(torch.randn(M, Kd, device=dev))
+            b = bf(torch.randn(N, Kd, device=dev) * 0.5)
+            ref = a.float() @ b.float().t()
+            A = a.t().contiguous() if a_mn else a
+            Bm = b.t().contiguous() if b_mn else b
+            out_f32 = kw.get("f32", False)
+            out = torch.empty(M, N, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
+            bias = torch.randn(N, device=dev) if kw.get("bias") else None
+            res = torch.randn(M, N, device=dev) if kw.get("res") else None
+            act = kw.get("act", 0)
+            if bias is not None:
+                ref = ref + bias
+            pre = ref.clone()
+            if act == 1:
+                ref = F.gelu(ref)
+            elif act == 2:
+                ref = F.relu(ref)
+            aux = None
+            aux_mode = kw.get("aux_mode", 0)
+            if aux_mode:
+                aux = bf(torch.randn(M, N, device=dev))
+                if aux_mode == 1:
+                    x = aux.float().requires_grad_(True)
+                    (gg,) = torch.autograd.grad(F.gelu(x).sum(), x)
+                    ref = ref * gg
+                else:
+                    ref = ref * (aux.float() > 0)
+            if res is not None:
+                ref = ref + res
+            out2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if kw.get("out2") else None
+            accumulate = kw.get("acc", False)
+            if accumulate:
+                base = torch.randn(M, N, device=dev)
+                out.copy_(base)
+                ref = ref + base
+            K.gemm(A, Bm, out, a_mn=a_mn, b_mn=b_mn, bias=bias, act=act, out2=out2, aux=aux, aux_mode=aux_mode,
+                   residual=res, accumulate=accumulate, split_k=kw.get("split_k", 0))
+            torch.cuda.synchronize()
+            report(f"gemm M{M} N{N} K{Kd} a_mn{int(a_mn)} b_mn{int(b_mn)} {kw}", rel(out, ref), 1e-2)
+            if out2 is not None:
+                report("   out2 (pre-activation)", rel(out2, pre), 1e-2)
+        run(f"gemm {M}x{N}x{Kd} {a_mn} {b_mn} {kw}", f)
+
+    case(128, 256, 64, False, False, f32=True)
+    case(128, 256, 256, False, False, f32=True)
+    case(256, 512, 768, False, False)
+    case(1000, 768, 768, False, False, bias=True, act=1, out2=True)
+    case(1000, 768, 3072, False, False, bias=True, res=True, f32=True)
+    case(128, 128, 128, False, False, f32=True)
+    case(300, 64, 256, False, False, f32=True)
+    case(128, 256, 64, False, True, f32=True)
+    case(1000, 768, 3072, False, True, aux_mode=1)
+    case(1000, 256, 6912, False, True, aux_mode=2)
+    case(128, 256, 64, True, False, f32=True)
+    case(128, 256, 64, True, True, f32=True)
+    case(768, 3072, 1000, True, True, f32=True, acc=True)
+    case(768, 768, 12608, True, True, f32=True, acc=True)
+    case(2304, 768, 4000, True, True, f32=True, acc=True, split_k=3)
+    case(12608, 768, 768, False, False, bias=True)
+    case(12608, 3072, 768, False, False, bias=True, act=1)
+
+    def patch_case():
+        Bn, T, D, Kd = 3, 196, 768, 768
+        a = bf(torch.randn(Bn * T, Kd, device=dev))
+        w = bf(torch.randn(D, Kd, device=dev) * 0.1)
+        bias = torch.randn(D, device=dev)
+        pos = torch.randn(T + 1, D, device=dev)
+        x = torch.zeros(Bn * (T + 1), D, device=dev)
+        K.gemm(a, w, x, bias=bias, residual=pos, row_tokens=T)
+        ref = (a.float() @ w.float().t() + bias).view(Bn, T, D) + pos[1:]
+        got = x.view(Bn, T + 1, D)[:, 1:]
+        report("gemm patch-embed row remap", rel(got, ref), 1e-2)
+        report("   cls rows untouched", x.view(Bn, T + 1, D)[:, 0].abs().max().item(), 0.0)
+    run("gemm patch", patch_case)
+
+
+def probe_ln():
+    def f():
+        for D in (768, 1024, 512):
+            M = 1000
+            x = torch.randn(M, D, device=dev) * 2 + 0.5
+            g = torch.randn(D, device=dev)
+            b = torch.randn(D, device=dev)
+            y = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+            yf = torch.empty(M, D, device=dev)
+            mean = torch.empty(M, device=dev)
+            rstd = torch.empty(M, device=dev)
+            K.layernorm_fwd(x, g, b, 1e-12, y, yf, mean, rstd)
+            ref = F.layer_norm(x, (D,), g, b, 1e-12)
+            report(f"ln fwd f32 D{D}", rel(yf, ref), 1e-5)
+            report(f"ln fwd bf16 D{D}", rel(y, ref), 1e-2)
+            xr = x.clone().requires_grad_(True)
+            gr = g.clone().requires_grad_(True)
+            br = b.clone().requires_grad_(True)
+            dy = torch.randn(M, D, device=dev)
+            F.layer_norm(xr, (D,), gr, br, 1e-12).backward(dy)
+            dxin = torch.randn(M, D, device=dev)
+            dx = torch.empty(M, D, device=dev)
+            dxb = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+            dg = torch.zeros(D, device=dev)
+            db = torch.zeros(D, device=dev)
+            K.layernorm_bwd(dy, x, g, mean, rstd, dxin, dx, dxb, dg, db)
+            report(f"ln bwd dx D{D}", rel(dx, xr.grad + dxin), 1e-4)
+            report(f"ln bwd dgamma D{D}", rel(dg, gr.grad), 1e-4)
+            report(f"ln bwd dbeta D{D}", rel(db, br.grad), 1e-4)
+            dyb = bf(dy)
+            dg.zero_(); db.zero_()
+            K.layernorm_bwd(dyb, x, g, mean, rstd, None, dx, None, dg, db)
+            xr.grad = None
+            F.layer_norm(xr, (D,), g, b, 1e-12).backward(dyb.float())
+            report(f"ln bwd dx (bf16 dy) D{D}", rel(dx, xr.grad), 1e-4)
+    run("ln", f)
+
+
+def probe_attn():
+    def case(Bn, N, H):
+        def f():
+            D = H * 64
+            qkv = bf(torch.randn(Bn, N, 3, H, 64, device=dev))
+            ctx = torch.empty(Bn, N, H, 64, device=dev, dtype=torch.bfloat16)
+            lse = torch.empty(Bn, H, N, device=dev)
+            K.attention_fwd(qkv, ctx, lse, Bn, N, H, 0.125)
+            q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).float().requires_grad_(True) for i in range(3)]
+            s = (q @ k.transpose(-1, -2)) * 0.125
+            ref = torch.softmax(s, -1) @ v
+            report(f"attn fwd B{Bn} N{N} H{H}", rel(ctx.permute(0, 2, 1, 3), ref), 1e-2)
+            report(f"attn lse B{Bn} N{N} H{H}", rel(lse, torch.logsumexp(s, -1)), 1e-3)
+            dctx = bf(torch.randn(Bn, N, H, 64, device=dev))
+            ref.backward(dctx.permute(0, 2, 1, 3).float())
+            dqkv = torch.zeros(Bn, N, 3, H, 64, device=dev, dtype=torch.bfloat16)
+            dq_acc = torch.empty(Bn, N, D, device=dev)
+            delta = torch.empty(Bn, H, N, device=dev)
+            K.attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_acc, delta, Bn, N, H, 0.125)
+            report(f"attn bwd dK B{Bn} N{N} H{H}", rel(dqkv[:, :, 1].permute(0, 2, 1, 3), k.grad), 2e-2)
+            report(f"attn bwd dV B{Bn} N{N} H{H}", rel(dqkv[:, :, 2].permute(0, 2, 1, 3), v.grad), 2e-2)
+            report(f"attn bwd dQ B{Bn} N{N} H{H}", rel(dq_acc.view(Bn, N, H, 64).permute(0, 2, 1, 3), q.grad), 2e-2)
+        run(f"attn {Bn} {N} {H}", f)
+
+    case(1, 128, 1)
+    case(2, 197, 12)
+    case(1, 64, 2)
+    case(2, 577, 4)
+    case(1, 1025, 2)
+
+
+def probe_head():
+    def f():
+        Bn, g, D, Fd, Cn = 2, 14, 768, 256, 17
+        T = g * g
+        tok = bf(torch.randn(Bn, T + 1, D, device=dev))
+        col = torch.empty(Bn * T, 9 * D, device=dev, dtype=torch.bfloat16)
+        K.head_im2col(tok, col, Bn, g, D)
+        feat = tok[:, 1:].float().transpose(1, 2).reshape(Bn, D, g, g)
+        w = torch.randn(Fd, D, 3, 3, device=dev) * 0.05
+        wp = torch.empty(Fd, 9 * D, device=dev, dtype=torch.bfloat16)
+        K.pack_conv3x3(w, wp)
+        ref = F.conv2d(feat, bf(w).float(), padding=1)  # [B,F,g,g]
+        got = (col.float() @ wp.float().t()).view(Bn, g, g, Fd).permute(0, 3, 1, 2)
+        report("head im2col+pack == conv3x3", rel(got, ref), 1e-3)
+        # col2im adjoint
+        dcol = bf(torch.randn(Bn * T, 9 * D, device=dev))
+        dtok = torch.empty(Bn, T + 1, D, device=dev)
+        K.head_col2im(dcol, dtok, Bn, g, D)
+        fr = feat.clone().requires_grad_(True)
+        colr = F.unfold(fr, 3, padding=1)  # [B, D*9, T] with (c,ky,kx) order
+        colr = colr.view(Bn, D, 9, T).permute(0, 3, 2, 1).reshape(Bn * T, 9 * D)
+        colr.backward(dcol.float())
+        refd = fr.grad.reshape(Bn, D, T).transpose(1, 2)
+        report("head col2im adjoint", rel(dtok[:, 1:], refd), 1e-2)
+        report("head col2im cls row zero", dtok[:, 0].abs().max().item(), 0.0)
+        # conv1x1
+        ft = bf(torch.relu(torch.randn(Bn * T, Fd, device=dev)))
+        w2 = torch.randn(Cn, Fd, device=dev) * 0.1
+        b2 = torch.randn(Cn, device=dev)
+        lg = torch.empty(Bn, Cn, g, g, device=dev)
+        K.conv1x1_fwd(ft, w2, b2, lg, Bn, g, Fd, Cn)
+        ref1 = (ft.float() @ w2.t() + b2).view(Bn, T, Cn).transpose(1, 2).reshape(Bn, Cn, g, g)
+        report("conv1x1 fwd", rel(lg, ref1), 1e-5)
+        dl = torch.randn(Bn, Cn, g, g, device=dev)
+        dfeat = torch.empty(Bn * T, Fd, device=dev, dtype=torch.bfloat16)
+        dw = torch.zeros(Cn, Fd, device=dev)
+        db = torch.zeros(Cn, device=dev)
+        K.conv1x1_bwd(dl, ft, w2, dfeat, dw, db, Bn, g, Fd, Cn)
+        dl2 = dl.view(Bn, Cn, T).transpose(1, 2).reshape(Bn * T, Cn)
+        report("conv1x1 bwd dfeat", rel(dfeat, (dl2 @ w2) * (ft.float() > 0)), 1e-2)
+        report("conv1x1 bwd dw", rel(dw, dl2.t() @ ft.float()), 1e-4)
+        report("conv1x1 bwd db", rel(db, dl2.sum(0)), 1e-4)
+        # patchify
+        img = torch.rand(Bn, 3, 224, 224, device=dev)
+        pm = torch.empty(Bn * T, 768, device=dev, dtype=torch.bfloat16)
+        K.patchify(img, pm, 16)
+        refp = F.unfold(img, 16, stride=16).transpose(1, 2).reshape(Bn * T, 768)
+        report("patchify", rel(pm, refp), 4e-3)
+        # colsum / embed_bwd / casts
+        x = bf(torch.randn(1000, 768, device=dev))
+        cs = torch.zeros(768, device=dev)
+        K.colsum(x, cs, accumulate=False)
+        report("colsum", rel(cs, x.float().sum(0)), 1e-4)
+        dx = torch.randn(Bn, T + 1, D, device=dev)
+        dcls = torch.zeros(D, device=dev)
+        dpos = torch.zeros(T + 1, D, device=dev)
+        K.embed_bwd(dx, dcls, dpos, Bn, T + 1, D)
+        report("embed_bwd dpos", rel(dpos, dx.sum(0)), 1e-5)
+        report("embed_bwd dcls", rel(dcls, dx[:, 0].sum(0)), 1e-5)
+        gpk = torch.randn(Fd, 9 * D, device=dev)
+        dwc = torch.zeros(Fd, D, 3, 3, device=dev)
+        K.unpack_conv3x3_grad(gpk, dwc)
+        report("unpack_conv3x3_grad", rel(dwc, gpk.view(Fd, 3, 3, D).permute(0, 3, 1, 2)), 0.0)
+    run("head", f)
+
+
+def probe_loss():
+    def f():
+        for (Bn, Cn, g, S) in ((2, 17, 14, 224), (1, 17, 32, 512), (2, 1, 28, 224)):
+            low = torch.randn(Bn, Cn, g, g, device=dev)
+            full = torch.empty(Bn, Cn, S, S, device=dev)
+            K.upsample_fwd(low, full)
+            ref = F.interpolate(low, size=(S, S), mode="bilinear", align_corners=False)
+            report(f"upsample fwd {Bn},{Cn},{g},{S}", (full - ref).abs().max().item(), 1e-5)
+            dfull = torch.randn(Bn, Cn, S, S, device=dev)
+            dlow = torch.empty_like(low)
+            K.upsample_bwd(dfull, dlow)
+            lr = low.clone().requires_grad_(True)
+            F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False).backward(dfull)
+            report(f"upsample bwd {Bn},{Cn},{g},{S}", rel(dlow, lr.grad), 1e-4)
+            mask = torch.empty(Bn, S, S, device=dev, dtype=torch.uint8)
+            K.upsample_argmax(low, mask)
+            refm = (ref[:, 0] > 0) if Cn == 1 else ref.argmax(1)
+            report(f"upsample argmax mismatch frac {Bn},{Cn},{g},{S}", (mask.long() != refm.long()).float().mean().item(), 1e-5)
+            if Cn > 1:
+                labels = torch.randint(0, Cn, (Bn, S, S), device=dev)
+                labels[0, :3, :5] = -100
+                ls = torch.zeros(2, device=dev)
+                dl = torch.zeros_like(low)
+                K.upsample_ce(low, labels, ls, dl)
+                lr.grad = None
+                lossr = F.cross_entropy(F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False), labels,
+                                        reduction="sum")
+                lossr.backward()
+                report(f"upsample_ce loss {Bn},{Cn},{g},{S}", abs(ls[0].item() - lossr.item()) / lossr.item(), 1e-5)
+                report(f"upsample_ce count", abs(ls[1].item() - (labels != -100).sum().item()), 0.0)
+                report(f"upsample_ce dlow {Bn},{Cn},{g},{S}", rel(dl, lr.grad), 1e-4)
+    run("loss/upsample", f)
+
+    def paed_bin():
+        Bn, g, S = 3, 14, 224
+        low = torch.randn(Bn, 1, g, g, device=dev) * 2
+        mask = (torch.rand(Bn, S, S, device=dev) > 0.7).float()
+        sdf_e = torch.rand(Bn, S, S, device=dev)
+        sdf_i = torch.rand(Bn, S, S, device=dev)
+        stats = torch.zeros(Bn, 8, device=dev)
+        keys = torch.zeros(Bn, dtype=torch.int64, device=dev)
+        K.paed_binary_stats(low, mask, sdf_e, sdf_i, stats, keys)
+        lr = low.clone().requires_grad_(True)
+        z = F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False)
+        p = torch.sigmoid(z)
+        t = mask[:, None]
+        sx = torch.tensor([[1, 0, -1], [2, 0, -2], [1, 0, -1]], device=dev, dtype=torch.float32).view(1, 1, 3, 3)
+        gx = F.conv2d(p, sx, padding=1)
+        gy = F.conv2d(p, sx.transpose(2, 3), padding=1)
+        edge = torch.sqrt(gx ** 2 + gy ** 2 + 1e-6)
+        mx = edge.view(Bn, -1).max(1)[0]
+        ref_stats = torch.stack([
+            F.binary_cross_entropy(p, t, reduction="none").view(Bn, -1).sum(1),
+            (p * t).view(Bn, -1).sum(1), p.view(Bn, -1).sum(1), t.view(Bn, -1).sum(1),
+            (sdf_i[:, None] * p).view(Bn, -1).sum(1), (sdf_e[:, None] * edge).view(Bn, -1).sum(1)], 1)
+        report("paed_binary stats", rel(stats[:, :6], ref_stats), 1e-4)
+        got_max = (keys >> 32).to(torch.int32).view(torch.float32)
+        report("paed_binary max edge", rel(got_max, mx), 1e-6)
+        coef = torch.randn(Bn, 8, device=dev)
+        coef[:, 3] = 0
+        coef[:, 7] = 0
+        L = (ref_stats * coef[:, :6]).sum() + (mx * coef[:, 6]).sum()
+        L.backward()
+        dlow = torch.zeros_like(low)
+        K.paed_binary_bwd(low, mask, sdf_e, sdf_i, coef, keys, dlow)
+        report("paed_binary bwd dlow", rel(dlow, lr.grad), 1e-3)
+    run("paed binary", paed_bin)
+
+    def paed_multi():
+        Bn, Cn, g, S = 2, 17, 14, 224
+        low = torch.randn(Bn, Cn, g, g, device=dev)
+        labels = torch.randint(0, Cn, (Bn, S, S), device=dev)
+        t1, t2, t3 = [torch.empty(Bn, Cn, S, S, device=dev) for _ in range(3)]
+        ls = torch.zeros(1, device=dev)
+        dlow = torch.zeros_like(low)
+        K.paed_multiclass(low, labels, t1, t2, t3, ls, dlow)
+        lr = low.clone().requires_grad_(True)
+        p = torch.softmax(F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False), 1)
+        m = F.one_hot(labels, Cn).permute(0, 3, 1, 2).float()
+        x = torch.arange(19, device=dev).float() - 9
+        gk = torch.exp(-(x ** 2) / 18)
+        k2 = gk[:, None] * gk[None, :]
+        k2 = (k2 / k2.sum())[None, None].repeat(Cn, 1, 1, 1)
+        base = (F.conv2d(m, k2, padding=9, groups=Cn) - F.conv2d(p, k2, padding=9, groups=Cn)).abs()
+        loss = (m * (1 - p) * base * 2).sum()
+        loss.backward()
+        report("paed_multiclass loss", abs(ls.item() - loss.item()) / abs(loss.item()), 1e-4)
+        report("paed_multiclass dlow", rel(dlow, lr.grad), 1e-3)
+    run("paed multiclass", paed_multi)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["ln", "gemm", "attn", "head", "loss"]
+    print("device:", torch.cuda.get_device_name(0), "SMs:", torch.cuda.get_device_properties(0).multi_processor_count)
+    for w in which:
+        {"gemm": probe_gemm, "ln": probe_ln, "attn": probe_attn, "head": probe_head, "loss": probe_loss}[w]()
+    nfail = sum(1 for r in RESULTS if not r[3])
+    print(f"SUMMARY: {len(RESULTS) - nfail} pass, {nfail} fail")

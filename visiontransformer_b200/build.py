@@ -1,0 +1,89 @@
+"""Builds libvitseg.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+Usage: python -m visiontransformer_b200.build [--force]
+Objects are cached under visiontransformer_b200/lib/obj and rebuilt when a source or header is newer.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIBPATH = os.path.join(LIBDIR, "libvitseg.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-I", INCLUDE,
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; libvitseg cannot be built")
+    return nvcc
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _newest_header_mtime() -> float:
+    m = 0.0
+    for d in (CSRC, INCLUDE):
+        for f in os.listdir(d):
+            if f.endswith((".cuh", ".h")):
+                m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return m
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_m = _newest_header_mtime()
+    jobs = []
+    objs = []
+    for src in _sources():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJDIR, src[:-3] + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
+            jobs.append((s, o))
+
+    def compile_one(job):
+        s, o = job
+        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {s}:\n{r.stdout}\n{r.stderr}")
+        return r.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for log in ex.map(compile_one, jobs):
+                if verbose and log:
+                    print(log)
+    if jobs or not os.path.exists(LIBPATH):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIBPATH, *objs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIBPATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

@@ -1,0 +1,515 @@
+// Fused multi-head self-attention forward and backward on tcgen05 tensor cores (head_dim 64, non-causal).
+// Replaces ViTSelfAttention.forward + sdpa_attention_forward (TF:220-251, SDPA:40-104) and their autograd.
+//
+// Layouts: qkv bf16 [B, N, 3, H, 64] (output of the fused QKV GEMM), ctx/dctx bf16 [B, N, H, 64],
+//          lse/delta fp32 [B, H, N].
+//
+// Forward: one CTA per (128-row query tile, head, batch).  Warps 0-3 are "softmax" warps: thread r owns query
+// row r (the TMEM lane it can read), so row max / row sum need no shuffles.  Warp 4 lane 0 drives TMA and issues
+// the MMAs:   S = Q K^T  (TMEM, fp32)  ->  P = exp2(S*scale*log2e - m) written as bf16 into 128B-swizzled smem
+//             O_j = P V_j (TMEM) accumulated in registers with the online-softmax rescale across KV blocks of 128.
+// K/V blocks whose tail is shorter than 128 keys use a narrower MMA (N resp. K rounded up to 16), so N=197 costs
+// 128+80 key columns, not 256.
+//
+// Backward: one CTA per (128-key block, head, batch) loops over query tiles:
+//   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse),  dS = P (dP - delta) scale      (registers -> smem, bf16)
+//   dV += P^T dO,  dK += dS^T Q   (TMEM accumulators over the query loop; P/dS/Q/dO read MN-major in place)
+//   dQ_i = dS K  -> fp32 atomics into dq_accum (one add per key block; converted to bf16 by the caller).
+#include "common.cuh"
+#include "../../include/vitseg.h"
+
+namespace vs {
+
+constexpr int kDH = 64;
+constexpr int kBQ = 128;
+constexpr int kBKV = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// write 32 consecutive bf16 (columns c32*32 .. +32 of row r) of a [128 x 128] bf16 tile stored as two
+// [128 rows x 128 B] 128B-swizzled halves
+__device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c32, const float (&f)[32]) {
+  uint8_t* base = tile + (c32 >> 1) * 16384;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t chunk = (c32 & 1) * 4 + q;
+    uint4 v = make_uint4(pack_bf16(f[8 * q], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
+                         pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
+    *reinterpret_cast<uint4*>(base + sw128_offset(r, chunk)) = v;
+  }
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+struct AttnFwdSmem {
+  static constexpr int kQ = 0;
+  static constexpr int kK = 16384;
+  static constexpr int kV = 32768;
+  static constexpr int kP = 49152;             // 32 KB
+  static constexpr int kBar = 49152 + 32768;   // barriers
+  static constexpr int kTotal = kBar + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(160, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
+                float* __restrict__ lse, int B, int N, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::kBar);
+  uint64_t* bar_k = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * kDH;
+  const int nblk = (N + kBKV - 1) / kBKV;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_qkv);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint8_t* sQ = smem + AttnFwdSmem::kQ;
+      uint8_t* sK = smem + AttnFwdSmem::kK;
+      uint8_t* sV = smem + AttnFwdSmem::kV;
+      uint8_t* sP = smem + AttnFwdSmem::kP;
+      mbar_expect_tx(bar_k, 2 * 16384);
+      tma_load_3d(sQ, &tmap_qkv, bar_k, h * kDH, q0, b);
+      tma_load_3d(sK, &tmap_qkv, bar_k, D + h * kDH, 0, b);
+      mbar_expect_tx(bar_v, 16384);
+      tma_load_3d(sV, &tmap_qkv, bar_v, 2 * D + h * kDH, 0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t ph = j & 1;
+        const int kv0 = j * kBKV;
+        const int ncols = min(kBKV, ((N - kv0) + 15) & ~15);
+        mbar_wait(bar_k, ph);
+        tc_fence_after();
+        {
+          const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
+          const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+          const uint64_t bd = umma_desc_sw128(smem_u32(sK), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc, k > 0);
+          umma_commit(bar_s);
+        }
+        // K_j is free once S is complete: prefetch K_{j+1}
+        mbar_wait(bar_s, ph);
+        if (j + 1 < nblk) {
+          mbar_expect_tx(bar_k, 16384);
+          tma_load_3d(sK, &tmap_qkv, bar_k, D + h * kDH, kv0 + kBKV, b);
+        }
+        mbar_wait(bar_p, ph);
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+        {
+          const uint32_t idesc = umma_idesc_bf16(kBQ, kDH, 0, 1);
+          for (int kk = 0; kk < ncols / 16; ++kk) {
+            const uint64_t ad = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(smem_u32(sV) + kk * 2048, 16384, 1024);
+            umma_bf16(tmem_o, ad, bd, idesc, kk > 0);
+          }
+          umma_commit(bar_o);
+        }
+        mbar_wait(bar_o, ph);
+        if (j + 1 < nblk) {
+          mbar_expect_tx(bar_v, 16384);
+          tma_load_3d(sV, &tmap_qkv, bar_v, 2 * D + h * kDH, kv0 + kBKV, b);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps
+    const int r = warp * 32 + lane;
+    const int q = q0 + r;
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    uint8_t* sP = smem + AttnFwdSmem::kP;
+    const float sl2 = scale * kLog2e;
+    float m_run = -INFINITY, l_run = 0.0f;
+    float o_acc[kDH];
+#pragma unroll
+    for (int i = 0; i < kDH; ++i) o_acc[i] = 0.0f;
+
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv0 = j * kBKV;
+      const int nvalid = min(kBKV, N - kv0);
+      const int ncols = (nvalid + 15) & ~15;
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      // pass 1: row max
+      float m_blk = -INFINITY;
+      for (int c = 0; c < ncols; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, m_blk * sl2);
+      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      float l_blk = 0.0f;
+      // pass 2: probabilities -> bf16 smem (A operand of P·V)
+      for (int c = 0; c < ncols; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float pv = (c + i < nvalid) ? exp2f(__uint_as_float(v[i]) * sl2 - m_new) : 0.0f;
+          f[i] = pv;
+          l_blk += pv;
+        }
+        store_row32_sw128(sP, r, c >> 5, f);
+      }
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      // O_j
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kDH; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_o + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * alpha + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    if (q < N) {
+      const float inv = 1.0f / l_run;
+      uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)b * N + q) * D + h * kDH);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_uint4(pack_bf16(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv),
+                            pack_bf16(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv),
+                            pack_bf16(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv),
+                            pack_bf16(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv));
+      if (lse != nullptr) lse[((size_t)b * H + h) * N + q] = (m_run + log2f(l_run)) * kLn2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]; one warp per (b,n,h) row of 64
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                  float* __restrict__ delta, int B, int N, int H) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long rows = (long long)B * N * H;
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t a = reinterpret_cast<const uint32_t*>(o + row * kDH)[lane];
+  const uint32_t g = reinterpret_cast<const uint32_t*>(dout + row * kDH)[lane];
+  const float2 af = unpack_bf16(a), gf = unpack_bf16(g);
+  float s = warp_sum(af.x * gf.x + af.y * gf.y);
+  if (lane == 0) {
+    const int hh = int(row % H);
+    const long long bn = row / H;
+    const int n = int(bn % N);
+    const int bb = int(bn / N);
+    delta[((size_t)bb * H + hh) * N + n] = s;
+  }
+}
+
+struct AttnBwdSmem {
+  static constexpr int kK = 0;
+  static constexpr int kV = 16384;
+  static constexpr int kQ = 32768;
+  static constexpr int kDO = 49152;
+  static constexpr int kP = 65536;             // 32 KB
+  static constexpr int kDS = 65536 + 32768;    // 32 KB
+  static constexpr int kBar = 65536 + 65536;
+  static constexpr int kTotal = kBar + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                float* __restrict__ dq_accum, int B, int N, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBar);
+  uint64_t* bar_kv = bars + 0;
+  uint64_t* bar_q = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_pds = bars + 3;
+  uint64_t* bar_dq = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * kBKV, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * kDH;
+  const int nq = (N + kBQ - 1) / kBQ;
+  const int nvalid_kv = min(kBKV, N - kv0);
+  const int ncols = (nvalid_kv + 15) & ~15;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_qkv);
+      tma_prefetch_desc(&tmap_do);
+      mbar_init(bar_kv, 1);
+      mbar_init(bar_q, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_pds, 128);
+      mbar_init(bar_dq, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
+                 tm_dq = tmem_base + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint8_t* sK = smem + AttnBwdSmem::kK;
+      uint8_t* sV = smem + AttnBwdSmem::kV;
+      uint8_t* sQ = smem + AttnBwdSmem::kQ;
+      uint8_t* sDO = smem + AttnBwdSmem::kDO;
+      const uint32_t aP = smem_u32(smem + AttnBwdSmem::kP);
+      const uint32_t aDS = smem_u32(smem + AttnBwdSmem::kDS);
+      mbar_expect_tx(bar_kv, 2 * 16384);
+      tma_load_3d(sK, &tmap_qkv, bar_kv, D + h * kDH, kv0, b);
+      tma_load_3d(sV, &tmap_qkv, bar_kv, 2 * D + h * kDH, kv0, b);
+      mbar_expect_tx(bar_q, 2 * 16384);
+      tma_load_3d(sQ, &tmap_qkv, bar_q, h * kDH, 0, b);
+      tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, 0, b);
+      mbar_wait(bar_kv, 0);
+      for (int i = 0; i < nq; ++i) {
+        const uint32_t ph = i & 1;
+        mbar_wait(bar_q, ph);
+        tc_fence_after();
+        {
+          // S = Q K^T and dP = dO V^T, both [128 q x ncols kv], reduction over head_dim
+          const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
+          const uint64_t qd = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+          const uint64_t kd = umma_desc_sw128(smem_u32(sK), 16, 1024);
+          const uint64_t od = umma_desc_sw128(smem_u32(sDO), 16, 1024);
+          const uint64_t vd = umma_desc_sw128(smem_u32(sV), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
+#pragma unroll
+          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
+          umma_commit(bar_s);
+        }
+        mbar_wait(bar_pds, ph);
+        tc_fence_after();
+        {
+          // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 128 keys, K = 128 queries)
+          const uint32_t idesc = umma_idesc_bf16(kBKV, kDH, 1, 1);
+#pragma unroll
+          for (int kk = 0; kk < kBQ / 16; ++kk) {
+            const uint64_t pd = umma_desc_sw128(aP + kk * 2048, 16384, 1024);
+            const uint64_t dod = umma_desc_sw128(smem_u32(sDO) + kk * 2048, 16384, 1024);
+            umma_bf16(tm_dv, pd, dod, idesc, (i > 0 || kk > 0));
+          }
+#pragma unroll
+          for (int kk = 0; kk < kBQ / 16; ++kk) {
+            const uint64_t dsd = umma_desc_sw128(aDS + kk * 2048, 16384, 1024);
+            const uint64_t qd = umma_desc_sw128(smem_u32(sQ) + kk * 2048, 16384, 1024);
+            umma_bf16(tm_dk, dsd, qd, idesc, (i > 0 || kk > 0));
+          }
+          // dQ_i = dS K : A = dS K-major (M = 128 queries, K = ncols keys), B = K MN-major (N = 64, K = keys)
+          const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
+          for (int kk = 0; kk < ncols / 16; ++kk) {
+            const uint64_t dsd = umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+            const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
+            umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
+          }
+          umma_commit(bar_dq);
+        }
+        mbar_wait(bar_dq, ph);
+        if (i + 1 < nq) {
+          mbar_expect_tx(bar_q, 2 * 16384);
+          tma_load_3d(sQ, &tmap_qkv, bar_q, h * kDH, (i + 1) * kBQ, b);
+          tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, (i + 1) * kBQ, b);
+        }
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    uint8_t* sP = smem + AttnBwdSmem::kP;
+    uint8_t* sDS = smem + AttnBwdSmem::kDS;
+    const float sl2 = scale * kLog2e;
+    for (int i = 0; i < nq; ++i) {
+      const uint32_t ph = i & 1;
+      const int q = i * kBQ + r;
+      const bool q_ok = q < N;
+      float lse2 = 0.0f, dlt = 0.0f;
+      if (q_ok) {
+        lse2 = lse[((size_t)b * H + h) * N + q] * kLog2e;
+        dlt = delta[((size_t)b * H + h) * N + q];
+      }
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      for (int c = 0; c < kBKV; c += 32) {
+        float pf[32], dsf[32];
+        if (c < ncols) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(tm_s + lane_off + c, sv);
+          tmem_ld32(tm_dp + lane_off + c, dv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const bool ok = q_ok && (c + k < nvalid_kv);
+            const float pv = ok ? exp2f(__uint_as_float(sv[k]) * sl2 - lse2) : 0.0f;
+            pf[k] = pv;
+            dsf[k] = pv * (__uint_as_float(dv[k]) - dlt) * scale;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { pf[k] = 0.0f; dsf[k] = 0.0f; }
+        }
+        store_row32_sw128(sP, r, c >> 5, pf);
+        store_row32_sw128(sDS, r, c >> 5, dsf);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+      mbar_wait(bar_dq, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kDH; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tm_dq + lane_off + c, v);
+        tmem_ld_wait();
+        if (q_ok) {
+          float* dst = dq_accum + ((size_t)b * N + q) * D + h * kDH + c;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k),
+                         "f"(__uint_as_float(v[4 * k])), "f"(__uint_as_float(v[4 * k + 1])),
+                         "f"(__uint_as_float(v[4 * k + 2])), "f"(__uint_as_float(v[4 * k + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+    }
+    // dK, dV rows: r <-> key kv0 + r.  All MMAs completed with the last bar_dq phase.
+    const int kv = kv0 + r;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t src = which == 0 ? tm_dk : tm_dv;
+      __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (which == 0 ? D : 2 * D) + h * kDH;
+#pragma unroll
+      for (int c = 0; c < kDH; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(src + lane_off + c, v);
+        tmem_ld_wait();
+        if (kv < N) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            d4[k] = make_uint4(pack_bf16(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
+                               pack_bf16(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
+                               pack_bf16(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                               pack_bf16(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+static int make_tok_tmap(CUtensorMap* m, const void* base, int B, int N, int row_elems) {
+  uint64_t dims[3] = {(uint64_t)row_elems, (uint64_t)N, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)row_elems * 2, (uint64_t)N * row_elems * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t B, int32_t N, int32_t H, float scale,
+                                void* stream) {
+  VS_CHECK_ARG(qkv && ctx, "vs_attention_fwd: null pointer");
+  VS_CHECK_ARG(B > 0 && N > 0 && H > 0, "vs_attention_fwd: bad shape");
+  VS_CHECK_ARG(B <= 65535 && H <= 65535, "vs_attention_fwd: B/H exceed grid limits");
+  VS_CHECK_ARG(sm_count() > 0, "vs_attention_fwd: no CUDA device");
+  CUtensorMap tm;
+  int rc = make_tok_tmap(&tm, qkv, B, N, 3 * H * kDH);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnFwdSmem::kTotal));
+    attr = true;
+  }
+  dim3 grid((N + kBQ - 1) / kBQ, H, B);
+  attn_fwd_kernel<<<grid, 160, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, (__nv_bfloat16*)ctx, lse, B, N, H,
+                                                                           scale);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                                float* dq_accum, float* delta, int32_t B, int32_t N, int32_t H, float scale,
+                                void* stream) {
+  VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && dq_accum && delta, "vs_attention_bwd: null pointer");
+  VS_CHECK_ARG(B > 0 && N > 0 && H > 0, "vs_attention_bwd: bad shape");
+  VS_CHECK_ARG(B <= 65535 && H <= 65535, "vs_attention_bwd: B/H exceed grid limits");
+  VS_CHECK_ARG(sm_count() > 0, "vs_attention_bwd: no CUDA device");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = H * kDH;
+  CUtensorMap tq, tdo;
+  int rc = make_tok_tmap(&tq, qkv, B, N, 3 * D);
+  if (rc) return rc;
+  rc = make_tok_tmap(&tdo, dctx, B, N, D);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnBwdSmem::kTotal));
+    attr = true;
+  }
+  const long long rows = (long long)B * N * H;
+  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx,
+                                                                delta, B, N, H);
+  VS_CHECK_LAUNCH();
+  VS_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * N * D * sizeof(float), st));
+  dim3 grid((N + kBKV - 1) / kBKV, H, B);
+  attn_bwd_kernel<<<grid, 160, AttnBwdSmem::kTotal, st>>>(tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, dq_accum, B, N, H,
+                                                          scale);
+  VS_CHECK_LAUNCH();
+  return 0;
+}

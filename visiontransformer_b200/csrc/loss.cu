@@ -1,0 +1,783 @@
+// Segmentation-head output stage: bilinear upsample (align_corners=False) fused with the losses.
+//   model/CE/classes.py:260        F.interpolate(out, size, mode='bilinear', align_corners=False)
+//   model/CE/classes.py:276-285    nn.CrossEntropyLoss on the upsampled logits
+//   model/PAED/classes.py:608-701  PAEDTrainer: sigmoid, BCE, Dice, Sobel edge x SDF terms
+//   model/PAED/classes.py:336-369  paed_loss_multiclass_soft on softmax probabilities
+//
+// The full-resolution logits [B,C,S,S] are only materialised for the inference contract; training kernels
+// interpolate on the fly from the low-resolution grid and reduce gradients back onto it.
+//
+// "Region" decomposition used by every adjoint: with P = S/g, output rows [ry*P - P/2, ry*P + P/2) (clipped) for
+// ry = 0..g all interpolate between the same two grid rows, likewise for columns.  One warp (or block) owns one
+// region, keeps per-lane partial sums and issues 4 atomics per class at the end.
+#include "common.cuh"
+#include "../../include/vitseg.h"
+
+namespace vs {
+
+// PyTorch's area_pixel_compute_source_index (align_corners=False) + the lambda computation of upsample_bilinear2d
+__device__ __forceinline__ void bil_coord(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * (dst + 0.5f) - 0.5f;
+  src = src < 0.0f ? 0.0f : src;
+  i0 = (int)src;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.0f - l1;
+}
+
+__device__ __forceinline__ float bil_sample(const float* plane, int g, int y0, int y1, float ly0, float ly1, int x0,
+                                            int x1, float lx0, float lx1) {
+  return ly0 * (lx0 * plane[y0 * g + x0] + lx1 * plane[y0 * g + x1]) +
+         ly1 * (lx0 * plane[y1 * g + x0] + lx1 * plane[y1 * g + x1]);
+}
+
+struct Region {
+  int b, y_lo, y_hi, x_lo, x_hi;
+};
+__device__ __forceinline__ Region region_of(long long rid, int g, int S) {
+  const int P = S / g, g1 = g + 1;
+  Region r;
+  const int rx = int(rid % g1);
+  const long long t = rid / g1;
+  const int ry = int(t % g1);
+  r.b = int(t / g1);
+  r.y_lo = max(0, ry * P - P / 2);
+  r.y_hi = min(S, ry * P + P / 2);
+  r.x_lo = max(0, rx * P - P / 2);
+  r.x_hi = min(S, rx * P + P / 2);
+  return r;
+}
+
+// ================================================================================================
+// plain upsample (inference contract), its adjoint, and the fused argmax
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+upsample_fwd_kernel(const float* __restrict__ low, float* __restrict__ full, int g, int S, int chunks) {
+  extern __shared__ float s_plane[];
+  const long long plane = blockIdx.x / chunks;
+  const int chunk = blockIdx.x % chunks;
+  for (int i = threadIdx.x; i < g * g; i += blockDim.x) s_plane[i] = low[plane * g * g + i];
+  __syncthreads();
+  const float scale = (float)g / (float)S;
+  const int S4 = S / 4;
+  const int rows_per = (S + chunks - 1) / chunks;
+  const int y_begin = chunk * rows_per, y_end = min(S, y_begin + rows_per);
+  float* out = full + plane * S * S;
+  for (int idx = y_begin * S4 + threadIdx.x; idx < y_end * S4; idx += blockDim.x) {
+    const int y = idx / S4, x4 = (idx - y * S4) * 4;
+    int y0, y1;
+    float ly0, ly1;
+    bil_coord(y, scale, g, y0, y1, ly0, ly1);
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int x0, x1;
+      float lx0, lx1;
+      bil_coord(x4 + k, scale, g, x0, x1, lx0, lx1);
+      r[k] = bil_sample(s_plane, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+    }
+    __stcs(reinterpret_cast<float4*>(out + (long long)y * S + x4), make_float4(r[0], r[1], r[2], r[3]));
+  }
+}
+
+// one warp per (plane, region): dlow[plane, cells] += sum over the region's pixels
+__global__ void __launch_bounds__(256)
+upsample_bwd_kernel(const float* __restrict__ dfull, float* __restrict__ dlow, long long planes, int g, int S) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nreg = planes * (g + 1) * (g + 1);
+  const long long rid = (long long)blockIdx.x * 8 + warp;
+  if (rid >= nreg) return;
+  const Region r = region_of(rid, g, S);  // r.b is the plane index here
+  const float scale = (float)g / (float)S;
+  const int w = r.x_hi - r.x_lo, h = r.y_hi - r.y_lo;
+  int y0, y1, x0, x1;
+  float t0, t1;
+  bil_coord(r.y_lo, scale, g, y0, y1, t0, t1);
+  bil_coord(r.x_lo, scale, g, x0, x1, t0, t1);
+  float a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+  const float* src = dfull + (long long)r.b * S * S;
+  for (int i = lane; i < w * h; i += 32) {
+    const int yy = r.y_lo + i / w, xx = r.x_lo + i % w;
+    int q0, q1;
+    float ly0, ly1, lx0, lx1;
+    bil_coord(yy, scale, g, q0, q1, ly0, ly1);
+    bil_coord(xx, scale, g, q0, q1, lx0, lx1);
+    const float v = src[(long long)yy * S + xx];
+    a00 += v * ly0 * lx0; a01 += v * ly0 * lx1; a10 += v * ly1 * lx0; a11 += v * ly1 * lx1;
+  }
+  a00 = warp_sum(a00); a01 = warp_sum(a01); a10 = warp_sum(a10); a11 = warp_sum(a11);
+  if (lane == 0) {
+    float* d = dlow + (long long)r.b * g * g;
+    atomicAdd(&d[y0 * g + x0], a00);
+    atomicAdd(&d[y0 * g + x1], a01);
+    atomicAdd(&d[y1 * g + x0], a10);
+    atomicAdd(&d[y1 * g + x1], a11);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask, int C, int g, int S, int chunks) {
+  extern __shared__ float s_low[];  // [C][g*g]
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  for (int i = threadIdx.x; i < C * g * g; i += blockDim.x) s_low[i] = low[(long long)b * C * g * g + i];
+  __syncthreads();
+  const float scale = (float)g / (float)S;
+  const int S4 = S / 4;
+  const int rows_per = (S + chunks - 1) / chunks;
+  const int y_begin = chunk * rows_per, y_end = min(S, y_begin + rows_per);
+  for (int idx = y_begin * S4 + threadIdx.x; idx < y_end * S4; idx += blockDim.x) {
+    const int y = idx / S4, x4 = (idx - y * S4) * 4;
+    int y0, y1;
+    float ly0, ly1;
+    bil_coord(y, scale, g, y0, y1, ly0, ly1);
+    uint8_t res[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int x0, x1;
+      float lx0, lx1;
+      bil_coord(x4 + k, scale, g, x0, x1, lx0, lx1);
+      if (C == 1) {
+        res[k] = bil_sample(s_low, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1) > 0.0f ? 1 : 0;
+      } else {
+        float best = -INFINITY;
+        int bi = 0;
+        for (int c = 0; c < C; ++c) {
+          const float v = bil_sample(s_low + c * g * g, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+          if (v > best) { best = v; bi = c; }
+        }
+        res[k] = (uint8_t)bi;
+      }
+    }
+    *reinterpret_cast<uchar4*>(mask + ((long long)b * S + y) * S + x4) = make_uchar4(res[0], res[1], res[2], res[3]);
+  }
+}
+
+// ================================================================================================
+// fused upsample + cross-entropy (+ gradient onto the low-res grid)
+// one warp per (image, region); lane = column within the region, rows strided; 2*C accumulators per lane
+// ================================================================================================
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+upsample_ce_kernel(const float* __restrict__ low, const long long* __restrict__ labels, float* __restrict__ loss_sum,
+                   float* __restrict__ dlow, int B, int C, int g, int S) {
+  __shared__ float s_cell[8][4][CMAX];
+  __shared__ float s_red[8][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nreg = (long long)B * (g + 1) * (g + 1);
+  const long long rid = (long long)blockIdx.x * 8 + warp;
+  float loss = 0.0f, cnt = 0.0f;
+  if (rid < nreg) {
+    const Region r = region_of(rid, g, S);
+    const float scale = (float)g / (float)S;
+    const int P = S / g;
+    int y0, y1, x0, x1;
+    float t0, t1;
+    bil_coord(r.y_lo, scale, g, y0, y1, t0, t1);
+    bil_coord(r.x_lo, scale, g, x0, x1, t0, t1);
+    const float* lb = low + (long long)r.b * C * g * g;
+    for (int c = lane; c < C; c += 32) {
+      s_cell[warp][0][c] = lb[c * g * g + y0 * g + x0];
+      s_cell[warp][1][c] = lb[c * g * g + y0 * g + x1];
+      s_cell[warp][2][c] = lb[c * g * g + y1 * g + x0];
+      s_cell[warp][3][c] = lb[c * g * g + y1 * g + x1];
+    }
+    __syncwarp();
+    const int xi = lane % P, roff = lane / P, rstep = (32 / P) > 0 ? (32 / P) : 1;
+    const int x = r.x_lo + xi;
+    const bool x_ok = (x < r.x_hi) && (lane < P * rstep);
+    int q0, q1;
+    float lx0 = 0.0f, lx1 = 0.0f;
+    if (x_ok) bil_coord(x, scale, g, q0, q1, lx0, lx1);
+    float acc0[CMAX], acc1[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
+    if (x_ok) {
+      for (int y = r.y_lo + roff; y < r.y_hi; y += rstep) {
+        float ly0, ly1;
+        bil_coord(y, scale, g, q0, q1, ly0, ly1);
+        const long long label = labels[((long long)r.b * S + y) * S + x];
+        const float w00 = ly0 * lx0, w01 = ly0 * lx1, w10 = ly1 * lx0, w11 = ly1 * lx1;
+        float z[CMAX];
+        float m = -INFINITY, zl = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          if (c < C) {
+            // same association order as PyTorch: ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11)
+            z[c] = ly0 * (lx0 * s_cell[warp][0][c] + lx1 * s_cell[warp][1][c]) +
+                   ly1 * (lx0 * s_cell[warp][2][c] + lx1 * s_cell[warp][3][c]);
+            m = fmaxf(m, z[c]);
+            if (c == label) zl = z[c];
+          }
+        }
+        (void)w00; (void)w01; (void)w10; (void)w11;
+        float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) { z[c] = expf(z[c] - m); s += z[c]; }
+        if (label != -100) {
+          loss += (m + logf(s)) - zl;
+          cnt += 1.0f;
+          const float inv = 1.0f / s;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c) {
+            if (c < C) {
+              const float gc = z[c] * inv - (c == label ? 1.0f : 0.0f);
+              acc0[c] += gc * ly0;
+              acc1[c] += gc * ly1;
+            }
+          }
+        }
+      }
+    }
+    if (dlow != nullptr) {
+      float* d = dlow + (long long)r.b * C * g * g;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          const float a00 = warp_sum(acc0[c] * lx0), a01 = warp_sum(acc0[c] * lx1);
+          const float a10 = warp_sum(acc1[c] * lx0), a11 = warp_sum(acc1[c] * lx1);
+          if (lane == 0) {
+            atomicAdd(&d[c * g * g + y0 * g + x0], a00);
+            atomicAdd(&d[c * g * g + y0 * g + x1], a01);
+            atomicAdd(&d[c * g * g + y1 * g + x0], a10);
+            atomicAdd(&d[c * g * g + y1 * g + x1], a11);
+          }
+        }
+      }
+    }
+  }
+  loss = warp_sum(loss);
+  cnt = warp_sum(cnt);
+  if (lane == 0) { s_red[warp][0] = loss; s_red[warp][1] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.0f, n = 0.0f;
+    for (int i = 0; i < 8; ++i) { l += s_red[i][0]; n += s_red[i][1]; }
+    atomicAdd(&loss_sum[0], l);
+    atomicAdd(&loss_sum[1], n);
+  }
+}
+
+// ================================================================================================
+// PAED binary (C = 1): one block per (image, region)
+// stats[b*8 + {0..6}] = {sum bce, sum p*t, sum p, sum t, sum sdf_int*p, sum sdf_ext*edge, -}; keys[b] = packed
+// (edge bits << 32 | ~pixel index) maximum, i.e. the per-image max edge and its FIRST arg-max (torch.max semantics).
+// ================================================================================================
+constexpr int kMaxP = 32;
+
+__device__ __forceinline__ float sigmoid_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// fills s_p[(hh+2*halo) x (ww+2*halo)] with sigmoid(upsampled logit) (0 outside the image)
+__device__ __forceinline__ void fill_prob_tile(float* s_p, const float* s_low, const Region& r, int halo, int g, int S) {
+  const float scale = (float)g / (float)S;
+  const int tw = (r.x_hi - r.x_lo) + 2 * halo, th = (r.y_hi - r.y_lo) + 2 * halo;
+  for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+    const int y = r.y_lo - halo + i / tw, x = r.x_lo - halo + i % tw;
+    float p = 0.0f;
+    if (y >= 0 && y < S && x >= 0 && x < S) {
+      int y0, y1, x0, x1;
+      float ly0, ly1, lx0, lx1;
+      bil_coord(y, scale, g, y0, y1, ly0, ly1);
+      bil_coord(x, scale, g, x0, x1, lx0, lx1);
+      p = sigmoid_acc(bil_sample(s_low, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1));
+    }
+    s_p[i] = p;
+  }
+}
+
+__device__ __forceinline__ void sobel_at(const float* s_p, int tw, int ty, int tx, float& gx, float& gy) {
+  const float a = s_p[(ty - 1) * tw + tx - 1], b = s_p[(ty - 1) * tw + tx], c = s_p[(ty - 1) * tw + tx + 1];
+  const float d = s_p[ty * tw + tx - 1], f = s_p[ty * tw + tx + 1];
+  const float gq = s_p[(ty + 1) * tw + tx - 1], hq = s_p[(ty + 1) * tw + tx], iq = s_p[(ty + 1) * tw + tx + 1];
+  gx = (a - c) + 2.0f * (d - f) + (gq - iq);
+  gy = (a + 2.0f * b + c) - (gq + 2.0f * hq + iq);
+}
+
+__global__ void __launch_bounds__(256)
+paed_binary_stats_kernel(const float* __restrict__ low, const float* __restrict__ mask, const float* __restrict__ sdf_ext,
+                         const float* __restrict__ sdf_int, float* __restrict__ stats,
+                         unsigned long long* __restrict__ keys, int B, int g, int S) {
+  __shared__ float s_low[kMaxP * kMaxP];
+  __shared__ float s_p[(kMaxP + 2) * (kMaxP + 2)];
+  __shared__ float s_red[8][6];
+  __shared__ unsigned long long s_key[8];
+  const Region r = region_of(blockIdx.x, g, S);
+  for (int i = threadIdx.x; i < g * g; i += blockDim.x) s_low[i] = low[(long long)r.b * g * g + i];
+  __syncthreads();
+  fill_prob_tile(s_p, s_low, r, 1, g, S);
+  __syncthreads();
+  const int w = r.x_hi - r.x_lo, h = r.y_hi - r.y_lo, tw = w + 2;
+  float acc[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long key = 0ull;
+  for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+    const int ly = i / w, lx = i % w;
+    const int y = r.y_lo + ly, x = r.x_lo + lx;
+    const long long pix = ((long long)r.b * S + y) * S + x;
+    const float p = s_p[(ly + 1) * tw + lx + 1];
+    const float t = mask[pix];
+    float gx, gy;
+    sobel_at(s_p, tw, ly + 1, lx + 1, gx, gy);
+    const float edge = sqrtf(gx * gx + gy * gy + 1e-6f);
+    const float lp = fmaxf(logf(p), -100.0f), lq = fmaxf(logf(1.0f - p), -100.0f);
+    acc[0] += -(t * lp + (1.0f - t) * lq);
+    acc[1] += p * t;
+    acc[2] += p;
+    acc[3] += t;
+    acc[4] += sdf_int[pix] * p;
+    acc[5] += sdf_ext[pix] * edge;
+    const unsigned long long k =
+        ((unsigned long long)__float_as_uint(edge) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(y * S + x));
+    key = k > key ? k : key;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) acc[i] = warp_sum(acc[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s_red[warp][i] = acc[i];
+    s_key[warp] = key;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float s = 0.0f;
+    for (int i = 0; i < 8; ++i) s += s_red[i][threadIdx.x];
+    atomicAdd(&stats[r.b * 8 + threadIdx.x], s);
+  }
+  if (threadIdx.x == 32) {
+    unsigned long long k = 0ull;
+    for (int i = 0; i < 8; ++i) k = s_key[i] > k ? s_key[i] : k;
+    atomicMax(&keys[r.b], k);
+  }
+}
+
+// coef[b*8 + {0..6}] = dL/d{bce_sum, inter, psum, tsum, int_sum, ext_sum, max_edge}
+__global__ void __launch_bounds__(256)
+paed_binary_bwd_kernel(const float* __restrict__ low, const float* __restrict__ mask, const float* __restrict__ sdf_ext,
+                       const float* __restrict__ sdf_int, const float* __restrict__ coef,
+                       const unsigned long long* __restrict__ keys, float* __restrict__ dlow, int B, int g, int S) {
+  __shared__ float s_low[kMaxP * kMaxP];
+  __shared__ float s_p[(kMaxP + 4) * (kMaxP + 4)];
+  __shared__ float s_gx[(kMaxP + 2) * (kMaxP + 2)];
+  __shared__ float s_gy[(kMaxP + 2) * (kMaxP + 2)];
+  __shared__ float s_red[8][4];
+  const Region r = region_of(blockIdx.x, g, S);
+  for (int i = threadIdx.x; i < g * g; i += blockDim.x) s_low[i] = low[(long long)r.b * g * g + i];
+  __syncthreads();
+  fill_prob_tile(s_p, s_low, r, 2, g, S);
+  __syncthreads();
+  const float* cf = coef + r.b * 8;
+  const float c_bce = cf[0], c_inter = cf[1], c_psum = cf[2], c_int = cf[4], c_ext = cf[5], c_max = cf[6];
+  const int arg = (int)(0xFFFFFFFFu - (uint32_t)(keys[r.b] & 0xFFFFFFFFull));
+  const int w = r.x_hi - r.x_lo, h = r.y_hi - r.y_lo;
+  const int tw2 = w + 4, tw1 = w + 2, th1 = h + 2;
+  // dL/dgx, dL/dgy on the region + 1 halo
+  for (int i = threadIdx.x; i < tw1 * th1; i += blockDim.x) {
+    const int ly = i / tw1, lx = i % tw1;
+    const int y = r.y_lo - 1 + ly, x = r.x_lo - 1 + lx;
+    float vx = 0.0f, vy = 0.0f;
+    if (y >= 0 && y < S && x >= 0 && x < S) {
+      float gx, gy;
+      sobel_at(s_p, tw2, ly + 1, lx + 1, gx, gy);
+      const float edge = sqrtf(gx * gx + gy * gy + 1e-6f);
+      float de = c_ext * sdf_ext[((long long)r.b * S + y) * S + x];
+      if (y * S + x == arg) de += c_max;
+      vx = de * gx / edge;
+      vy = de * gy / edge;
+    }
+    s_gx[i] = vx;
+    s_gy[i] = vy;
+  }
+  __syncthreads();
+  const float scale = (float)g / (float)S;
+  int y0, y1, x0, x1;
+  float t0, t1;
+  bil_coord(r.y_lo, scale, g, y0, y1, t0, t1);
+  bil_coord(r.x_lo, scale, g, x0, x1, t0, t1);
+  float a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+  for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+    const int ly = i / w, lx = i % w;
+    const int y = r.y_lo + ly, x = r.x_lo + lx;
+    const long long pix = ((long long)r.b * S + y) * S + x;
+    const float p = s_p[(ly + 2) * tw2 + lx + 2];
+    const float t = mask[pix];
+    float dp = c_bce * (p - t) / fmaxf(p * (1.0f - p), 1e-12f) + c_inter * t + c_psum + c_int * sdf_int[pix];
+    const int cy = ly + 1, cx = lx + 1;  // position in the halo-1 tiles
+#define GX(dy, dx) s_gx[(cy + (dy)) * tw1 + cx + (dx)]
+#define GY(dy, dx) s_gy[(cy + (dy)) * tw1 + cx + (dx)]
+    dp += (GX(1, 1) - GX(1, -1)) + 2.0f * (GX(0, 1) - GX(0, -1)) + (GX(-1, 1) - GX(-1, -1));
+    dp += (GY(1, 1) + 2.0f * GY(1, 0) + GY(1, -1)) - (GY(-1, 1) + 2.0f * GY(-1, 0) + GY(-1, -1));
+#undef GX
+#undef GY
+    const float dz = dp * p * (1.0f - p);
+    int q0, q1;
+    float ly0, ly1, lx0, lx1;
+    bil_coord(y, scale, g, q0, q1, ly0, ly1);
+    bil_coord(x, scale, g, q0, q1, lx0, lx1);
+    a00 += dz * ly0 * lx0; a01 += dz * ly0 * lx1; a10 += dz * ly1 * lx0; a11 += dz * ly1 * lx1;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  a00 = warp_sum(a00); a01 = warp_sum(a01); a10 = warp_sum(a10); a11 = warp_sum(a11);
+  if (lane == 0) { s_red[warp][0] = a00; s_red[warp][1] = a01; s_red[warp][2] = a10; s_red[warp][3] = a11; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.0f;
+    for (int i = 0; i < 8; ++i) s += s_red[i][threadIdx.x];
+    const int yy = (threadIdx.x & 2) ? y1 : y0, xx = (threadIdx.x & 1) ? x1 : x0;
+    atomicAdd(&dlow[(long long)r.b * g * g + yy * g + xx], s);
+  }
+}
+
+// ================================================================================================
+// PAED multi-class soft loss
+// ================================================================================================
+// per pixel softmax of the upsampled logits; mode 0: out[c] = onehot - p ; mode 1: loss + u = 2 m (1-p) sign(t)
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+pm_pixel_kernel(const float* __restrict__ low, const long long* __restrict__ labels, const float* __restrict__ tin,
+                float* __restrict__ out, float* __restrict__ loss_sum, int mode, int C, int g, int S, int chunks) {
+  extern __shared__ float s_low[];
+  __shared__ float s_red[8];
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  for (int i = threadIdx.x; i < C * g * g; i += blockDim.x) s_low[i] = low[(long long)b * C * g * g + i];
+  __syncthreads();
+  const float scale = (float)g / (float)S;
+  const int rows_per = (S + chunks - 1) / chunks;
+  const int y_begin = chunk * rows_per, y_end = min(S, y_begin + rows_per);
+  float loss = 0.0f;
+  for (int idx = y_begin * S + threadIdx.x; idx < y_end * S; idx += blockDim.x) {
+    const int y = idx / S, x = idx - y * S;
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    bil_coord(y, scale, g, y0, y1, ly0, ly1);
+    bil_coord(x, scale, g, x0, x1, lx0, lx1);
+    float z[CMAX];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        z[c] = bil_sample(s_low + c * g * g, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+        m = fmaxf(m, z[c]);
+      }
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { z[c] = expf(z[c] - m); s += z[c]; }
+    const float inv = 1.0f / s;
+    const long long label = labels[((long long)b * S + y) * S + x];
+    const long long base = (long long)b * C * S * S + (long long)y * S + x;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        const float p = z[c] * inv;
+        const float mk = (c == label) ? 1.0f : 0.0f;
+        const long long o = base + (long long)c * S * S;
+        if (mode == 0) {
+          out[o] = mk - p;
+        } else {
+          const float t = tin[o];
+          const float pen = mk * (1.0f - p) * 2.0f;
+          loss += pen * fabsf(t);
+          out[o] = pen * (t > 0.0f ? 1.0f : (t < 0.0f ? -1.0f : 0.0f));
+        }
+      }
+  }
+  if (mode == 1) {
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float l = 0.0f;
+      for (int i = 0; i < 8; ++i) l += s_red[i];
+      atomicAdd(loss_sum, l);
+    }
+  }
+}
+
+// 19-tap normalised Gaussian (sigma 3) along x (dir 0) or y (dir 1), zero padding; one output per thread
+__constant__ float c_gauss[19];
+__global__ void __launch_bounds__(256)
+blur1d_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int S, int dir) {
+  const long long total = planes * S * S;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = int(idx % S);
+    const long long t = idx / S;
+    const int y = int(t % S);
+    const long long pb = (t / S) * S * S;
+    float s = 0.0f;
+    if (dir == 0) {
+      const float* row = in + pb + (long long)y * S;
+#pragma unroll
+      for (int k = 0; k < 19; ++k) {
+        const int xx = x + k - 9;
+        if (xx >= 0 && xx < S) s += c_gauss[k] * row[xx];
+      }
+    } else {
+      const float* colp = in + pb + x;
+#pragma unroll
+      for (int k = 0; k < 19; ++k) {
+        const int yy = y + k - 9;
+        if (yy >= 0 && yy < S) s += c_gauss[k] * colp[(long long)yy * S];
+      }
+    }
+    out[idx] = s;
+  }
+}
+
+// backward: dp_c = -2 m_c |t_c| - blur(u)_c ; dz_c = p_c (dp_c - sum_k p_k dp_k) ; reduce onto the grid by region
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+pm_bwd_kernel(const float* __restrict__ low, const long long* __restrict__ labels, const float* __restrict__ tt,
+              const float* __restrict__ bu, float* __restrict__ dlow, int B, int C, int g, int S) {
+  __shared__ float s_cell[8][4][CMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nreg = (long long)B * (g + 1) * (g + 1);
+  const long long rid = (long long)blockIdx.x * 8 + warp;
+  if (rid >= nreg) return;
+  const Region r = region_of(rid, g, S);
+  const float scale = (float)g / (float)S;
+  const int P = S / g;
+  int y0, y1, x0, x1;
+  float t0, t1;
+  bil_coord(r.y_lo, scale, g, y0, y1, t0, t1);
+  bil_coord(r.x_lo, scale, g, x0, x1, t0, t1);
+  const float* lb = low + (long long)r.b * C * g * g;
+  for (int c = lane; c < C; c += 32) {
+    s_cell[warp][0][c] = lb[c * g * g + y0 * g + x0];
+    s_cell[warp][1][c] = lb[c * g * g + y0 * g + x1];
+    s_cell[warp][2][c] = lb[c * g * g + y1 * g + x0];
+    s_cell[warp][3][c] = lb[c * g * g + y1 * g + x1];
+  }
+  __syncwarp();
+  const int xi = lane % P, roff = lane / P, rstep = (32 / P) > 0 ? (32 / P) : 1;
+  const int x = r.x_lo + xi;
+  const bool x_ok = (x < r.x_hi) && (lane < P * rstep);
+  int q0, q1;
+  float lx0 = 0.0f, lx1 = 0.0f;
+  if (x_ok) bil_coord(x, scale, g, q0, q1, lx0, lx1);
+  float acc0[CMAX], acc1[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
+  if (x_ok) {
+    for (int y = r.y_lo + roff; y < r.y_hi; y += rstep) {
+      float ly0, ly1;
+      bil_coord(y, scale, g, q0, q1, ly0, ly1);
+      const long long label = labels[((long long)r.b * S + y) * S + x];
+      const long long base = (long long)r.b * C * S * S + (long long)y * S + x;
+      float z[CMAX];
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          z[c] = ly0 * (lx0 * s_cell[warp][0][c] + lx1 * s_cell[warp][1][c]) +
+                 ly1 * (lx0 * s_cell[warp][2][c] + lx1 * s_cell[warp][3][c]);
+          m = fmaxf(m, z[c]);
+        }
+      float s = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { z[c] = expf(z[c] - m); s += z[c]; }
+      const float inv = 1.0f / s;
+      float dp[CMAX];
+      float dot = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          z[c] *= inv;  // p_c
+          const long long o = base + (long long)c * S * S;
+          float d = -bu[o];
+          if (c == label) d -= 2.0f * fabsf(tt[o]);
+          dp[c] = d;
+          dot += z[c] * d;
+        }
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          const float dz = z[c] * (dp[c] - dot);
+          acc0[c] += dz * ly0;
+          acc1[c] += dz * ly1;
+        }
+    }
+  }
+  float* d = dlow + (long long)r.b * C * g * g;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c)
+    if (c < C) {
+      const float a00 = warp_sum(acc0[c] * lx0), a01 = warp_sum(acc0[c] * lx1);
+      const float a10 = warp_sum(acc1[c] * lx0), a11 = warp_sum(acc1[c] * lx1);
+      if (lane == 0) {
+        atomicAdd(&d[c * g * g + y0 * g + x0], a00);
+        atomicAdd(&d[c * g * g + y0 * g + x1], a01);
+        atomicAdd(&d[c * g * g + y1 * g + x0], a10);
+        atomicAdd(&d[c * g * g + y1 * g + x1], a11);
+      }
+    }
+}
+
+static int check_grid(const char* fn, int B, int C, int g, int S) {
+  if (B <= 0 || C <= 0 || g <= 0 || S <= 0 || S % g != 0) { set_error("%s: bad shape B=%d C=%d g=%d S=%d", fn, B, C, g, S); return -1; }
+  const int P = S / g;
+  if (P < 2 || P > kMaxP || (P & (P - 1)) != 0) { set_error("%s: S/g=%d must be a power of two in [2,%d]", fn, P, kMaxP); return -1; }
+  if (S % 4 != 0) { set_error("%s: S must be a multiple of 4", fn); return -1; }
+  if (sm_count() <= 0) return -1;
+  return 0;
+}
+
+static int ensure_gauss() {
+  static bool done = false;
+  if (done) return 0;
+  // model/PAED/classes.py:341-345 builds the 19x19 kernel in fp32 as g g^T / sum(g g^T) == (g/sum g)(g/sum g)^T
+  float gk[19];
+  float sum = 0.0f;
+  for (int k = 0; k < 19; ++k) { const float x = float(k - 9); gk[k] = expf(-(x * x) / 18.0f); sum += gk[k]; }
+  for (int k = 0; k < 19; ++k) gk[k] /= sum;
+  VS_CHECK_CUDA(cudaMemcpyToSymbol(c_gauss, gk, sizeof(gk)));
+  done = true;
+  return 0;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_upsample_bilinear_fwd(const float* low, float* full, int32_t B, int32_t C, int32_t g, int32_t S,
+                                        void* stream) {
+  VS_CHECK_ARG(low && full, "vs_upsample_bilinear_fwd: null pointer");
+  if (int rc = check_grid("vs_upsample_bilinear_fwd", B, C, g, S)) return rc;
+  const long long planes = (long long)B * C;
+  int chunks = 1;
+  while (planes * chunks < (long long)sm_count() * 4 && chunks < S / 8) chunks *= 2;
+  upsample_fwd_kernel<<<(unsigned)(planes * chunks), 256, g * g * sizeof(float), (cudaStream_t)stream>>>(low, full, g, S,
+                                                                                                        chunks);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_upsample_bilinear_bwd(const float* dfull, float* dlow, int32_t B, int32_t C, int32_t g, int32_t S,
+                                        void* stream) {
+  VS_CHECK_ARG(dfull && dlow, "vs_upsample_bilinear_bwd: null pointer");
+  if (int rc = check_grid("vs_upsample_bilinear_bwd", B, C, g, S)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long planes = (long long)B * C;
+  VS_CHECK_CUDA(cudaMemsetAsync(dlow, 0, (size_t)planes * g * g * sizeof(float), st));
+  const long long nreg = planes * (g + 1) * (g + 1);
+  upsample_bwd_kernel<<<(unsigned)((nreg + 7) / 8), 256, 0, st>>>(dfull, dlow, planes, g, S);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, int32_t C, int32_t g, int32_t S,
+                                  void* stream) {
+  VS_CHECK_ARG(low && mask, "vs_upsample_argmax: null pointer");
+  if (int rc = check_grid("vs_upsample_argmax", B, C, g, S)) return rc;
+  VS_CHECK_ARG(C <= 255, "vs_upsample_argmax: C must be <= 255");
+  const size_t smem = (size_t)C * g * g * sizeof(float);
+  VS_CHECK_ARG(smem <= 200 * 1024, "vs_upsample_argmax: C*g*g too large");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(upsample_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int chunks = 1;
+  while ((long long)B * chunks < (long long)sm_count() * 4 && chunks < S / 8) chunks *= 2;
+  upsample_argmax_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(low, mask, C, g, S, chunks);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_upsample_ce(const float* low, const int64_t* labels, float* loss_sum, float* dlow, int32_t B,
+                              int32_t C, int32_t g, int32_t S, void* stream) {
+  VS_CHECK_ARG(low && labels && loss_sum, "vs_upsample_ce: null pointer");
+  if (int rc = check_grid("vs_upsample_ce", B, C, g, S)) return rc;
+  VS_CHECK_ARG(C <= 32, "vs_upsample_ce: C must be <= 32");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nreg = (long long)B * (g + 1) * (g + 1);
+  const unsigned grid = (unsigned)((nreg + 7) / 8);
+  const long long* lab = (const long long*)labels;
+  if (C == 1) upsample_ce_kernel<1><<<grid, 256, 0, st>>>(low, lab, loss_sum, dlow, B, C, g, S);
+  else if (C <= 4) upsample_ce_kernel<4><<<grid, 256, 0, st>>>(low, lab, loss_sum, dlow, B, C, g, S);
+  else if (C <= 8) upsample_ce_kernel<8><<<grid, 256, 0, st>>>(low, lab, loss_sum, dlow, B, C, g, S);
+  else if (C <= 17) upsample_ce_kernel<17><<<grid, 256, 0, st>>>(low, lab, loss_sum, dlow, B, C, g, S);
+  else upsample_ce_kernel<32><<<grid, 256, 0, st>>>(low, lab, loss_sum, dlow, B, C, g, S);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_paed_binary_stats(const float* low, const float* mask, const float* sdf_ext, const float* sdf_int,
+                                    float* stats, uint64_t* keys, int32_t B, int32_t g, int32_t S, void* stream) {
+  VS_CHECK_ARG(low && mask && sdf_ext && sdf_int && stats && keys, "vs_paed_binary_stats: null pointer");
+  if (int rc = check_grid("vs_paed_binary_stats", B, 1, g, S)) return rc;
+  VS_CHECK_ARG(g <= kMaxP, "vs_paed_binary_stats: g must be <= %d", kMaxP);
+  const long long nreg = (long long)B * (g + 1) * (g + 1);
+  paed_binary_stats_kernel<<<(unsigned)nreg, 256, 0, (cudaStream_t)stream>>>(low, mask, sdf_ext, sdf_int, stats,
+                                                                            (unsigned long long*)keys, B, g, S);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_paed_binary_bwd(const float* low, const float* mask, const float* sdf_ext, const float* sdf_int,
+                                  const float* coef, const uint64_t* keys, float* dlow, int32_t B, int32_t g, int32_t S,
+                                  void* stream) {
+  VS_CHECK_ARG(low && mask && sdf_ext && sdf_int && coef && keys && dlow, "vs_paed_binary_bwd: null pointer");
+  if (int rc = check_grid("vs_paed_binary_bwd", B, 1, g, S)) return rc;
+  VS_CHECK_ARG(g <= kMaxP, "vs_paed_binary_bwd: g must be <= %d", kMaxP);
+  const long long nreg = (long long)B * (g + 1) * (g + 1);
+  paed_binary_bwd_kernel<<<(unsigned)nreg, 256, 0, (cudaStream_t)stream>>>(low, mask, sdf_ext, sdf_int, coef,
+                                                                          (const unsigned long long*)keys, dlow, B, g, S);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int CMAX>
+static int paed_multiclass_impl(const float* low, const long long* labels, float* t1, float* t2, float* t3,
+                                float* loss_sum, float* dlow, int B, int C, int g, int S, cudaStream_t st) {
+  const int nsm = sm_count();
+  const size_t smem = (size_t)C * g * g * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(pm_pixel_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int chunks = 1;
+  while ((long long)B * chunks < (long long)nsm * 4 && chunks < S / 4) chunks *= 2;
+  const long long planes = (long long)B * C;
+  const long long total = planes * S * S;
+  long long bg = (total + 255) / 256;
+  if (bg > (long long)nsm * 32) bg = (long long)nsm * 32;
+  // t1 = onehot - p ; t2 = blur_x(t1) ; t1 = blur_y(t2) = t
+  pm_pixel_kernel<CMAX><<<B * chunks, 256, smem, st>>>(low, labels, nullptr, t1, nullptr, 0, C, g, S, chunks);
+  blur1d_kernel<<<(unsigned)bg, 256, 0, st>>>(t1, t2, planes, S, 0);
+  blur1d_kernel<<<(unsigned)bg, 256, 0, st>>>(t2, t1, planes, S, 1);
+  // loss and u -> t2
+  pm_pixel_kernel<CMAX><<<B * chunks, 256, smem, st>>>(low, labels, t1, t2, loss_sum, 1, C, g, S, chunks);
+  VS_CHECK_LAUNCH();
+  if (dlow != nullptr) {
+    // blur(u): t3 = blur_x(t2) ; t2 = blur_y(t3)
+    blur1d_kernel<<<(unsigned)bg, 256, 0, st>>>(t2, t3, planes, S, 0);
+    blur1d_kernel<<<(unsigned)bg, 256, 0, st>>>(t3, t2, planes, S, 1);
+    const long long nreg = (long long)B * (g + 1) * (g + 1);
+    pm_bwd_kernel<CMAX><<<(unsigned)((nreg + 7) / 8), 256, 0, st>>>(low, labels, t1, t2, dlow, B, C, g, S);
+    VS_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int vs_paed_multiclass(const float* low, const int64_t* labels, float* t1, float* t2, float* t3,
+                                  float* loss_sum, float* dlow, int32_t B, int32_t C, int32_t g, int32_t S,
+                                  void* stream) {
+  VS_CHECK_ARG(low && labels && t1 && t2 && loss_sum, "vs_paed_multiclass: null pointer");
+  VS_CHECK_ARG(dlow == nullptr || t3 != nullptr, "vs_paed_multiclass: t3 scratch required for the backward pass");
+  if (int rc = check_grid("vs_paed_multiclass", B, C, g, S)) return rc;
+  VS_CHECK_ARG(C <= 32, "vs_paed_multiclass: C must be <= 32");
+  if (int rc = ensure_gauss()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long* lab = (const long long*)labels;
+  if (C <= 4) return paed_multiclass_impl<4>(low, lab, t1, t2, t3, loss_sum, dlow, B, C, g, S, st);
+  if (C <= 17) return paed_multiclass_impl<17>(low, lab, t1, t2, t3, loss_sum, dlow, B, C, g, S, st);
+  return paed_multiclass_impl<32>(low, lab, t1, t2, t3, loss_sum, dlow, B, C, g, S, st);
+}

@@ -1,0 +1,463 @@
+// Glue kernels around the GEMMs (all HBM-bound, 128-bit vectorised where layouts allow):
+//   bias-gradient column sums, patch extraction, CLS/position rows, embedding backward, segmentation-head
+//   im2col / col2im, the 1x1 classifier conv (forward + backward with fused ReLU'), weight casts / packing.
+// Reference anchors: TF:100-128,153-167 (embeddings); model/CE/classes.py:240-244,250-257 (seg head).
+#include "common.cuh"
+#include "../../include/vitseg.h"
+
+namespace vs {
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a bf16 matrix: out[n] (+)= sum_m x[m, n]
+// block = 256 threads = 32 column groups (8 bf16 = 16 B each) x 8 row lanes; grid.y splits the rows
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int M, int N, float* __restrict__ out) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cg) * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  if (col < N) {
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + (long long)r * ldx + col);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(w[i]);
+        acc[2 * i] += f.x;
+        acc[2 * i + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rl][cg * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;  // 256 columns of this block
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i][c];
+  const int gc = blockIdx.x * 256 + c;
+  if (gc < N) atomicAdd(&out[gc], s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify: NCHW fp32 image -> bf16 [B*T, 3*P*P] with K = (c, ph, pw); 4 pixels per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int P) {
+  const int gp = S / P;
+  const int K = 3 * P * P;
+  const long long total = (long long)B * gp * gp * (K / 4);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k4 = int(idx % (K / 4));
+    const long long row = idx / (K / 4);
+    const int k = k4 * 4;
+    const int c = k / (P * P), rem = k - c * P * P, ph = rem / P, pw = rem - ph * P;
+    const int tx = int(row % gp);
+    const long long t2 = row / gp;
+    const int ty = int(t2 % gp), b = int(t2 / gp);
+    const float4 v = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + c) * S + (ty * P + ph)) * S + tx * P + pw);
+    *reinterpret_cast<uint2*>(out + row * K + k) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
+                                int B, int T1, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int b = idx / D, d = idx - b * D;
+  x[(long long)b * T1 * D + d] = cls[d] + pos[d];
+}
+
+// dpos[t, d] += sum_b dx[b, t, d]; dcls[d] += sum_b dx[b, 0, d]
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos, int B,
+                                 int T1, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over T1 * D/4
+  const int D4 = D / 4;
+  if (idx >= T1 * D4) return;
+  float4 s = make_float4(0, 0, 0, 0);
+  const float4* p = reinterpret_cast<const float4*>(dx) + idx;
+  for (int b = 0; b < B; ++b) {
+    const float4 v = p[(long long)b * T1 * D4];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  float4* dp = reinterpret_cast<float4*>(dpos) + idx;
+  float4 o = *dp;
+  o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+  *dp = o;
+  if (idx < D4) {
+    float4* dc = reinterpret_cast<float4*>(dcls) + idx;
+    float4 c = *dc;
+    c.x += s.x; c.y += s.y; c.z += s.z; c.w += s.w;
+    *dc = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg head: im2col of the token grid (CLS dropped), 3x3 window, zero padding; K = (ky, kx, c)
+// ------------------------------------------------------------------------------------------------
+__global__ void head_im2col_kernel(const __nv_bfloat16* __restrict__ tok, __nv_bfloat16* __restrict__ col, int B, int g,
+                                   int D) {
+  const int D8 = D / 8;
+  const long long total = (long long)B * g * g * 9 * D8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(idx % D8);
+    long long r = idx / D8;
+    const int kk = int(r % 9);
+    r /= 9;
+    const int x = int(r % g);
+    r /= g;
+    const int y = int(r % g), b = int(r / g);
+    const int yy = y + kk / 3 - 1, xx = x + kk % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < g && xx >= 0 && xx < g)
+      v = *reinterpret_cast<const uint4*>(tok + ((long long)b * (g * g + 1) + 1 + yy * g + xx) * D + c8 * 8);
+    *reinterpret_cast<uint4*>(col + (((long long)b * g + y) * g + x) * (9LL * D) + (long long)kk * D + c8 * 8) = v;
+  }
+}
+
+// adjoint of im2col: dtok[b, 1 + y*g + x, c] = sum_{ky,kx} dcol[(b, y-ky+1, x-kx+1), (ky,kx,c)]; CLS row = 0
+__global__ void head_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dtok, int B, int g, int D) {
+  const int D8 = D / 8;
+  const int T1 = g * g + 1;
+  const long long total = (long long)B * T1 * D8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(idx % D8);
+    const long long r = idx / D8;
+    const int t = int(r % T1), b = int(r / T1);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    if (t > 0) {
+      const int y = (t - 1) / g, x = (t - 1) % g;
+#pragma unroll
+      for (int kk = 0; kk < 9; ++kk) {
+        const int yy = y - (kk / 3) + 1, xx = x - (kk % 3) + 1;
+        if (yy >= 0 && yy < g && xx >= 0 && xx < g) {
+          const uint4 v = *reinterpret_cast<const uint4*>(dcol + (((long long)b * g + yy) * g + xx) * (9LL * D) +
+                                                          (long long)kk * D + c8 * 8);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack_bf16(w[i]);
+            acc[2 * i] += f.x;
+            acc[2 * i + 1] += f.y;
+          }
+        }
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(dtok + r * D + c8 * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 classifier conv: one warp per pixel, weights in shared memory
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv1x1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ logits, int B, int T, int F, int C) {
+  extern __shared__ float s_w[];  // [C][F]
+  for (int i = threadIdx.x; i < C * F; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long npix = (long long)B * T;
+  for (long long pix = (long long)blockIdx.x * 8 + warp; pix < npix; pix += (long long)gridDim.x * 8) {
+    const int b = int(pix / T), t = int(pix - (long long)b * T);
+    for (int f0 = 0; f0 < F; f0 += 256) {
+      // each lane holds 8 consecutive features of this 256-chunk
+      float x[8];
+      const int f = f0 + lane * 8;
+      if (f < F) {
+        const uint4 v = *reinterpret_cast<const uint4*>(feat + pix * F + f);
+        const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 q = unpack_bf16(ww[i]);
+          x[2 * i] = q.x;
+          x[2 * i + 1] = q.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.0f;
+      }
+      for (int c = 0; c < C; ++c) {
+        float s = 0.0f;
+        if (f < F) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s += x[i] * s_w[c * F + f + i];
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+          float* o = logits + ((long long)b * C + c) * T + t;
+          if (f0 == 0) *o = s + bias[c];
+          else *o += s;
+        }
+      }
+    }
+  }
+}
+
+// thread f owns feature f: dfeat[pix,f] = relu'(feat) * sum_c dl[pix,c] w[c,f];  dw[c,f] += sum_pix dl[pix,c] feat[pix,f]
+constexpr int kMaxClasses = 32;
+__global__ void __launch_bounds__(256)
+conv1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ feat, const float* __restrict__ w,
+                   __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db, int B, int T,
+                   int F, int C) {
+  __shared__ float s_dl[64][kMaxClasses];
+  const int f = threadIdx.x;
+  const long long npix = (long long)B * T;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+  float wc[kMaxClasses], acc[kMaxClasses];
+#pragma unroll
+  for (int c = 0; c < kMaxClasses; ++c) {
+    wc[c] = (c < C && f < F) ? w[c * F + f] : 0.0f;
+    acc[c] = 0.0f;
+  }
+  float dbacc = 0.0f;  // thread c (< C) accumulates db[c]
+  for (long long base = p0; base < p1; base += 64) {
+    const int n = int(min((long long)64, p1 - base));
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * C; i += blockDim.x) {
+      const int pi = i / C, c = i - pi * C;
+      const long long pix = base + pi;
+      const int b = int(pix / T), t = int(pix - (long long)b * T);
+      s_dl[pi][c] = dlogits[((long long)b * C + c) * T + t];
+    }
+    __syncthreads();
+    if (f < C)
+      for (int pi = 0; pi < n; ++pi) dbacc += s_dl[pi][f];
+    if (f < F) {
+      for (int pi = 0; pi < n; ++pi) {
+        const float x = __bfloat162float(feat[(base + pi) * F + f]);
+        float d = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kMaxClasses; ++c) {
+          if (c < C) {
+            const float g = s_dl[pi][c];
+            d += g * wc[c];
+            acc[c] += g * x;
+          }
+        }
+        dfeat[(base + pi) * F + f] = __float2bfloat16(x > 0.0f ? d : 0.0f);
+      }
+    }
+  }
+  if (f < F) {
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < C) atomicAdd(&dw[c * F + f], acc[c]);
+  }
+  if (f < C) atomicAdd(&db[f], dbacc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// casts / packing
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+__global__ void cast_rows_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                 long long ldd, int M, int D) {
+  const int D4 = D / 4;
+  const long long total = (long long)M * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D4;
+    const int c = int(i - r * D4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+    *reinterpret_cast<uint2*>(dst + r * ldd + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// OIHW fp32 [O, I, 3, 3] -> bf16 [O, (ky, kx, I)]
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I) {
+  const long long total = (long long)O * I * 9;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = int(idx % I);
+    const long long r = idx / I;
+    const int kk = int(r % 9), o = int(r / 9);
+    out[idx] = __float2bfloat16(w[((long long)o * I + i) * 9 + kk]);
+  }
+}
+// grad fp32 [O, (ky,kx,I)] -> dw OIHW +=
+__global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ g, float* __restrict__ dw, int O, int I) {
+  const long long total = (long long)O * I * 9;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kk = int(idx % 9);
+    const long long r = idx / 9;
+    const int i = int(r % I), o = int(r / I);
+    dw[idx] += g[((long long)o * 9 + kk) * I + i];
+  }
+}
+
+static inline int grid_for(long long total, int block, int nsm) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)nsm * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate,
+                              void* stream) {
+  VS_CHECK_ARG(x && out && M > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0, "vs_colsum_bf16: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_colsum_bf16: no CUDA device");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) VS_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
+  const int gx = (N + 255) / 256;
+  int gy = (nsm * 4 + gx - 1) / gx;
+  if (gy > (M + 63) / 64) gy = (M + 63) / 64;
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, M, N, out);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_patchify(const float* img, void* out, int32_t B, int32_t S, int32_t P, void* stream) {
+  VS_CHECK_ARG(img && out && B > 0 && S > 0 && P >= 4 && P % 4 == 0 && S % P == 0, "vs_patchify: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_patchify: no CUDA device");
+  const long long total = (long long)B * (S / P) * (S / P) * (3 * P * P / 4);
+  patchify_kernel<<<grid_for(total, 256, nsm), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, S, P);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_cls_rows(const float* cls, const float* pos, float* x, int32_t B, int32_t T1, int32_t D, void* stream) {
+  VS_CHECK_ARG(cls && pos && x && B > 0 && T1 > 0 && D > 0, "vs_cls_rows: bad arguments");
+  VS_CHECK_ARG(sm_count() > 0, "vs_cls_rows: no CUDA device");
+  cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, pos, x, B, T1, D);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_embed_bwd(const float* dx, float* dcls, float* dpos, int32_t B, int32_t T1, int32_t D, void* stream) {
+  VS_CHECK_ARG(dx && dcls && dpos && B > 0 && T1 > 0 && D % 4 == 0, "vs_embed_bwd: bad arguments");
+  VS_CHECK_ARG(sm_count() > 0, "vs_embed_bwd: no CUDA device");
+  const int total = T1 * (D / 4);
+  embed_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dx, dcls, dpos, B, T1, D);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_head_im2col(const void* tokens, void* col, int32_t B, int32_t g, int32_t D, void* stream) {
+  VS_CHECK_ARG(tokens && col && B > 0 && g > 0 && D % 8 == 0, "vs_head_im2col: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_head_im2col: no CUDA device");
+  const long long total = (long long)B * g * g * 9 * (D / 8);
+  head_im2col_kernel<<<grid_for(total, 256, nsm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)tokens,
+                                                                                  (__nv_bfloat16*)col, B, g, D);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_head_col2im(const void* dcol, float* dtokens, int32_t B, int32_t g, int32_t D, void* stream) {
+  VS_CHECK_ARG(dcol && dtokens && B > 0 && g > 0 && D % 8 == 0, "vs_head_col2im: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_head_col2im: no CUDA device");
+  const long long total = (long long)B * (g * g + 1) * (D / 8);
+  head_col2im_kernel<<<grid_for(total, 256, nsm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, dtokens, B,
+                                                                                  g, D);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_conv1x1_fwd(const void* feat, const float* w, const float* b, float* logits, int32_t B, int32_t g,
+                              int32_t F, int32_t C, void* stream) {
+  VS_CHECK_ARG(feat && w && b && logits && B > 0 && g > 0 && F % 8 == 0 && C > 0, "vs_conv1x1_fwd: bad arguments");
+  VS_CHECK_ARG((size_t)C * F * 4 <= 96 * 1024, "vs_conv1x1_fwd: C*F too large for shared memory");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_conv1x1_fwd: no CUDA device");
+  const size_t smem = (size_t)C * F * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(conv1x1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const long long npix = (long long)B * g * g;
+  int grid = (int)((npix + 7) / 8);
+  if (grid > nsm * 8) grid = nsm * 8;
+  conv1x1_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)feat, w, b, logits, B, g * g, F, C);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_conv1x1_bwd(const float* dlogits, const void* feat, const float* w, void* dfeat, float* dw, float* db,
+                              int32_t B, int32_t g, int32_t F, int32_t C, void* stream) {
+  VS_CHECK_ARG(dlogits && feat && w && dfeat && dw && db, "vs_conv1x1_bwd: null pointer");
+  VS_CHECK_ARG(B > 0 && g > 0 && F > 0 && F <= 256 && C > 0 && C <= kMaxClasses,
+               "vs_conv1x1_bwd: unsupported shape (F<=256, C<=%d)", kMaxClasses);
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_conv1x1_bwd: no CUDA device");
+  const long long npix = (long long)B * g * g;
+  int grid = nsm * 2;
+  if (grid > (npix + 63) / 64) grid = (int)((npix + 63) / 64);
+  conv1x1_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dlogits, (const __nv_bfloat16*)feat, w,
+                                                             (__nv_bfloat16*)dfeat, dw, db, B, g * g, F, C);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  VS_CHECK_ARG(src && dst && n > 0, "vs_cast_f32_bf16: bad arguments");
+  VS_CHECK_ARG(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "vs_cast_f32_bf16: misaligned");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_cast_f32_bf16: no CUDA device");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256, nsm), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_cast_bf16_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t M, int32_t D,
+                                 void* stream) {
+  VS_CHECK_ARG(src && dst && M > 0 && D > 0 && D % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vs_cast_bf16_rows: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_cast_bf16_rows: no CUDA device");
+  cast_rows_kernel<<<grid_for((long long)M * D / 4, 256, nsm), 256, 0, (cudaStream_t)stream>>>(
+      src, lds, (__nv_bfloat16*)dst, ldd, M, D);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_pack_conv3x3(const float* w, void* out, int32_t O, int32_t I, void* stream) {
+  VS_CHECK_ARG(w && out && O > 0 && I > 0, "vs_pack_conv3x3: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_pack_conv3x3: no CUDA device");
+  pack_conv3x3_kernel<<<grid_for((long long)O * I * 9, 256, nsm), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out,
+                                                                                                 O, I);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_unpack_conv3x3_grad(const float* g, float* dw, int32_t O, int32_t I, void* stream) {
+  VS_CHECK_ARG(g && dw && O > 0 && I > 0, "vs_unpack_conv3x3_grad: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_unpack_conv3x3_grad: no CUDA device");
+  unpack_conv3x3_grad_kernel<<<grid_for((long long)O * I * 9, 256, nsm), 256, 0, (cudaStream_t)stream>>>(g, dw, O, I);
+  VS_CHECK_LAUNCH();
+  return 0;
+}

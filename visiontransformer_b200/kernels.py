@@ -1,0 +1,217 @@
+"""Tensor-level wrappers over the C ABI (one Python function per vs_* entry point).
+
+These are plumbing: argument checking, pointer extraction, the current stream.  Every function requires CUDA
+tensors and raises otherwise — nothing here falls back to PyTorch math."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, ptr, require_cuda, stream
+
+BF16, F32 = torch.bfloat16, torch.float32
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+AUX_NONE, AUX_GELU_GRAD, AUX_RELU_MASK = 0, 1, 2
+
+
+def _rowmajor(t: torch.Tensor, what: str) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, f"{what}: expected a row-major 2-D view, got strides {t.stride()}"
+    return t.stride(0)
+
+
+def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=None, aux=None, aux_mode=AUX_NONE,
+         residual=None, row_tokens=0, accumulate=False, split_k=0, M=None, N=None, K=None):
+    """out[M,N] = epilogue(sum_k A(m,k) B(n,k)); see include/vitseg.h:vs_gemm_desc.
+
+    a: bf16 [M,K] (or [K,M] when a_mn); b: bf16 [N,K] (or [K,N] when b_mn); out: bf16 or fp32 2-D view."""
+    require_cuda(a, "gemm")
+    assert a.dtype == BF16 and b.dtype == BF16
+    if M is None:
+        M = a.shape[1] if a_mn else a.shape[0]
+    if K is None:
+        K = a.shape[0] if a_mn else a.shape[1]
+    if N is None:
+        N = b.shape[1] if b_mn else b.shape[0]
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.a_mn_major, d.b_mn_major = int(a_mn), int(b_mn)
+    d.A, d.lda = ptr(a), _rowmajor(a, "A")
+    d.B, d.ldb = ptr(b), _rowmajor(b, "B")
+    d.out, d.ldo = ptr(out), _rowmajor(out, "out")
+    assert out.dtype in (BF16, F32)
+    d.out_dtype = 1 if out.dtype == F32 else 0
+    d.accumulate = int(accumulate)
+    if bias is not None:
+        assert bias.dtype == F32 and bias.is_contiguous()
+    d.bias = ptr(bias)
+    d.act = act
+    if out2 is not None:
+        assert out2.dtype == BF16
+        d.out2, d.ldo2 = ptr(out2), _rowmajor(out2, "out2")
+    if aux is not None:
+        assert aux.dtype == BF16
+        d.aux, d.ldaux = ptr(aux), _rowmajor(aux, "aux")
+    d.aux_mode = aux_mode
+    if residual is not None:
+        assert residual.dtype == F32
+        d.residual, d.ldr = ptr(residual), _rowmajor(residual, "residual")
+    d.row_tokens = row_tokens
+    d.split_k = split_k
+    check(_lib.load().vs_gemm_bf16(C.byref(d), stream()), "vs_gemm_bf16")
+    return out
+
+
+def colsum(x, out, accumulate=True):
+    require_cuda(x, "colsum")
+    assert x.dtype == BF16 and out.dtype == F32
+    check(_lib.load().vs_colsum_bf16(ptr(x), _rowmajor(x, "x"), x.shape[0], x.shape[1], ptr(out), int(accumulate),
+                                    stream()), "vs_colsum_bf16")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
+    require_cuda(x, "layernorm_fwd")
+    assert x.dtype == F32 and x.is_contiguous()
+    M, D = x.shape
+    check(_lib.load().vs_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), eps, M, D, ptr(y_bf16), ptr(y_f32), ptr(mean),
+                                      ptr(rstd), stream()), "vs_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_bf16, dgamma, dbeta):
+    require_cuda(x, "layernorm_bwd")
+    M, D = x.shape
+    assert dy.is_contiguous() and dy.dtype in (BF16, F32)
+    check(_lib.load().vs_layernorm_bwd(ptr(dy), int(dy.dtype == F32), ptr(x), ptr(gamma), ptr(mean), ptr(rstd),
+                                      ptr(dx_in), M, D, ptr(dx_out), ptr(dx_bf16), ptr(dgamma), ptr(dbeta), stream()),
+          "vs_layernorm_bwd")
+
+
+def attention_fwd(qkv, ctx, lse, B, N, H, scale):
+    require_cuda(qkv, "attention_fwd")
+    assert qkv.dtype == BF16 and qkv.is_contiguous() and ctx.is_contiguous()
+    check(_lib.load().vs_attention_fwd(ptr(qkv), ptr(ctx), ptr(lse), B, N, H, scale, stream()), "vs_attention_fwd")
+
+
+def attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_accum, delta, B, N, H, scale):
+    require_cuda(qkv, "attention_bwd")
+    check(_lib.load().vs_attention_bwd(ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse), ptr(dqkv), ptr(dq_accum), ptr(delta), B,
+                                      N, H, scale, stream()), "vs_attention_bwd")
+
+
+def patchify(img, out, P):
+    require_cuda(img, "patchify")
+    assert img.dtype == F32 and img.is_contiguous()
+    B, _, S, _ = img.shape
+    check(_lib.load().vs_patchify(ptr(img), ptr(out), B, S, P, stream()), "vs_patchify")
+
+
+def cls_rows(cls, pos, x, B, T1, D):
+    check(_lib.load().vs_cls_rows(ptr(cls), ptr(pos), ptr(x), B, T1, D, stream()), "vs_cls_rows")
+
+
+def embed_bwd(dx, dcls, dpos, B, T1, D):
+    check(_lib.load().vs_embed_bwd(ptr(dx), ptr(dcls), ptr(dpos), B, T1, D, stream()), "vs_embed_bwd")
+
+
+def head_im2col(tokens, col, B, g, D):
+    check(_lib.load().vs_head_im2col(ptr(tokens), ptr(col), B, g, D, stream()), "vs_head_im2col")
+
+
+def head_col2im(dcol, dtokens, B, g, D):
+    check(_lib.load().vs_head_col2im(ptr(dcol), ptr(dtokens), B, g, D, stream()), "vs_head_col2im")
+
+
+def conv1x1_fwd(feat, w, b, logits, B, g, F, Cn):
+    check(_lib.load().vs_conv1x1_fwd(ptr(feat), ptr(w), ptr(b), ptr(logits), B, g, F, Cn, stream()), "vs_conv1x1_fwd")
+
+
+def conv1x1_bwd(dlogits, feat, w, dfeat, dw, db, B, g, F, Cn):
+    check(_lib.load().vs_conv1x1_bwd(ptr(dlogits), ptr(feat), ptr(w), ptr(dfeat), ptr(dw), ptr(db), B, g, F, Cn,
+                                    stream()), "vs_conv1x1_bwd")
+
+
+def upsample_fwd(low, full):
+    require_cuda(low, "upsample_fwd")
+    B, Cn, g, _ = low.shape
+    S = full.shape[-1]
+    assert low.is_contiguous() and full.is_contiguous() and low.dtype == F32 and full.dtype == F32
+    check(_lib.load().vs_upsample_bilinear_fwd(ptr(low), ptr(full), B, Cn, g, S, stream()), "vs_upsample_bilinear_fwd")
+    return full
+
+
+def upsample_bwd(dfull, dlow):
+    B, Cn, g, _ = dlow.shape
+    S = dfull.shape[-1]
+    assert dfull.is_contiguous() and dfull.dtype == F32
+    check(_lib.load().vs_upsample_bilinear_bwd(ptr(dfull), ptr(dlow), B, Cn, g, S, stream()), "vs_upsample_bilinear_bwd")
+    return dlow
+
+
+def upsample_argmax(low, mask):
+    require_cuda(low, "upsample_argmax")
+    B, Cn, g, _ = low.shape
+    S = mask.shape[-1]
+    assert mask.dtype == torch.uint8 and mask.is_contiguous() and low.is_contiguous()
+    check(_lib.load().vs_upsample_argmax(ptr(low), ptr(mask), B, Cn, g, S, stream()), "vs_upsample_argmax")
+    return mask
+
+
+def upsample_ce(low, labels, loss_sum, dlow):
+    require_cuda(low, "upsample_ce")
+    B, Cn, g, _ = low.shape
+    S = labels.shape[-1]
+    assert labels.dtype == torch.int64 and labels.is_contiguous() and low.is_contiguous()
+    check(_lib.load().vs_upsample_ce(ptr(low), ptr(labels), ptr(loss_sum), ptr(dlow), B, Cn, g, S, stream()),
+          "vs_upsample_ce")
+
+
+def paed_binary_stats(low, mask, sdf_ext, sdf_int, stats, keys):
+    require_cuda(low, "paed_binary_stats")
+    B, _, g, _ = low.shape
+    S = mask.shape[-1]
+    for t in (low, mask, sdf_ext, sdf_int):
+        assert t.dtype == F32 and t.is_contiguous()
+    check(_lib.load().vs_paed_binary_stats(ptr(low), ptr(mask), ptr(sdf_ext), ptr(sdf_int), ptr(stats), ptr(keys), B, g,
+                                          S, stream()), "vs_paed_binary_stats")
+
+
+def paed_binary_bwd(low, mask, sdf_ext, sdf_int, coef, keys, dlow):
+    B, _, g, _ = low.shape
+    S = mask.shape[-1]
+    assert coef.dtype == F32 and coef.is_contiguous()
+    check(_lib.load().vs_paed_binary_bwd(ptr(low), ptr(mask), ptr(sdf_ext), ptr(sdf_int), ptr(coef), ptr(keys),
+                                        ptr(dlow), B, g, S, stream()), "vs_paed_binary_bwd")
+
+
+def paed_multiclass(low, labels, t1, t2, t3, loss_sum, dlow):
+    require_cuda(low, "paed_multiclass")
+    B, Cn, g, _ = low.shape
+    S = labels.shape[-1]
+    assert labels.dtype == torch.int64 and labels.is_contiguous() and low.is_contiguous()
+    check(_lib.load().vs_paed_multiclass(ptr(low), ptr(labels), ptr(t1), ptr(t2), ptr(t3), ptr(loss_sum), ptr(dlow), B,
+                                        Cn, g, S, stream()), "vs_paed_multiclass")
+
+
+def cast_bf16(src, dst):
+    require_cuda(src, "cast_bf16")
+    assert src.dtype == F32 and dst.dtype == BF16 and src.is_contiguous() and dst.is_contiguous()
+    check(_lib.load().vs_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream()), "vs_cast_f32_bf16")
+
+
+def cast_bf16_rows(src, dst):
+    M, D = src.shape
+    check(_lib.load().vs_cast_bf16_rows(ptr(src), _rowmajor(src, "src"), ptr(dst), _rowmajor(dst, "dst"), M, D,
+                                       stream()), "vs_cast_bf16_rows")
+
+
+def pack_conv3x3(w, out):
+    O, I = w.shape[0], w.shape[1]
+    assert w.is_contiguous()
+    check(_lib.load().vs_pack_conv3x3(ptr(w), ptr(out), O, I, stream()), "vs_pack_conv3x3")
+
+
+def unpack_conv3x3_grad(g, dw):
+    O, I = dw.shape[0], dw.shape[1]
+    check(_lib.load().vs_unpack_conv3x3_grad(ptr(g), ptr(dw), O, I, stream()), "vs_unpack_conv3x3_grad")
