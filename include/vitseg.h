@@ -51,8 +51,8 @@ int vs_device_sm_count(void);
  *   v *= gelu'(aux[m,n])  | v = aux[m,n]>0?v:0 (aux_mode 1 | 2; aux bf16 [M, ldaux])
  *   v += residual[rm, n]                       (residual != NULL; fp32, ld ldr)
  *   store to out (out_dtype 0 = bf16, 1 = fp32); accumulate != 0: atomic fp32 add (split-K / grad accumulation)
- * Row remap (patch embedding, TF:117-124): row_tokens = T > 0 writes GEMM row r to output row r + r/T + 1
- *   and reads residual row (r % T) + 1 (the position embedding); 0 = identity.
+ * Broadcast residual (patch embedding + position embedding, TF:117-124): row_tokens = T1 > 0 reads residual row
+ *   (m % T1), i.e. a [T1, N] table shared by every image; 0 = residual row m.
  * split_k: 0 = automatic (only >1 when accumulate != 0), else the number of K partitions.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct vs_gemm_desc {
@@ -112,14 +112,18 @@ int vs_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const f
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding glue (TF:100-128, 153-167)
- *   vs_patchify: image fp32 NCHW [B,3,S,S] -> bf16 patch matrix [B*T, 3*P*P], K ordered (c,ph,pw) = the
- *                row-major flattening of projection.weight [D,3,P,P].
+ *   vs_patchify: image fp32 NCHW [B,3,S,S] -> bf16 patch matrix [B*(T+1), 3*P*P], K ordered (c,ph,pw) = the
+ *                row-major flattening of projection.weight [D,3,P,P].  Row b*(T+1)+1+t holds patch t; the CLS
+ *                rows b*(T+1) are never written (the caller zeroes the buffer once) so that the projection GEMM,
+ *                its wgrad and the token matrix share one row indexing.
  *   vs_cls_rows: x[b, 0, :] = cls[:] + pos[0, :]   (x fp32 [B, T+1, D])
- *   vs_embed_bwd: dcls[D] += sum_b dx[b,0,:];  dpos[T+1, D] += sum_b dx[b,:,:]
+ *   vs_embed_bwd: dcls[D] += sum_b dx[b,0,:];  dpos[T+1, D] += sum_b dx[b,:,:];
+ *                 dbias[D] += sum_{b, t>=1} dx[b,t,:]  (patch projection bias)
  * ------------------------------------------------------------------------------------------------ */
 int vs_patchify(const float* img, void* out, int32_t B, int32_t S, int32_t P, void* stream);
 int vs_cls_rows(const float* cls, const float* pos, float* x, int32_t B, int32_t T1, int32_t D, void* stream);
-int vs_embed_bwd(const float* dx, float* dcls, float* dpos, int32_t B, int32_t T1, int32_t D, void* stream);
+int vs_embed_bwd(const float* dx, float* dcls, float* dpos, float* dbias, int32_t B, int32_t T1, int32_t D,
+                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Segmentation head (model/CE/classes.py:240-244,250-257)
@@ -181,6 +185,12 @@ int vs_paed_binary_bwd(const float* low, const float* mask, const float* sdf_ext
  * ------------------------------------------------------------------------------------------------ */
 int vs_paed_multiclass(const float* low, const int64_t* labels, float* t1, float* t2, float* t3, float* loss_sum,
                        float* dlow, int32_t B, int32_t C, int32_t g, int32_t S, void* stream);
+
+/* dense form of the same loss for callers holding [B,C,S,S] one-hot mask and probability tensors (the free
+ * function model/PAED/classes.py:336-369; sigma fixed at 3): loss_sum[0] += sum(penalty * |blur(msk - prob)|) with
+ * penalty = 2 msk (1 - prob) when class_penalty else 1; dprob (nullable) = d(sum)/d prob (overwritten). */
+int vs_paed_multiclass_dense(const float* msk, const float* prob, float* t1, float* t2, float* t3, float* loss_sum,
+                             float* dprob, int32_t B, int32_t C, int32_t S, int32_t class_penalty, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight shadows: fp32 master -> bf16 copy (one pass), plus utility conversions.

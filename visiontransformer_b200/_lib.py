@@ -46,7 +46,7 @@ _SIGS = {
                          c_float, c_void_p],
     "vs_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_cls_rows": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
-    "vs_embed_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "vs_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_head_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_head_col2im": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_conv1x1_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -60,6 +60,8 @@ _SIGS = {
                            c_void_p],
     "vs_paed_multiclass": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                            c_int, c_void_p],
+    "vs_paed_multiclass_dense": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_int, c_int, c_void_p],
     "vs_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "vs_cast_bf16_rows": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p],
     "vs_pack_conv3x3": [c_void_p, c_void_p, c_int, c_int, c_void_p],

@@ -182,11 +182,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc_fence_after();
       const int r = m0 + quad * 32 + lane;
       const bool row_ok = r < p.M;
-      long long orow = r, rrow = r;
-      if (p.row_tokens > 0) {
-        orow = (long long)r + r / p.row_tokens + 1;
-        rrow = (r % p.row_tokens) + 1;
-      }
+      const long long orow = r;
+      const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
       const bool add_bias = (p.bias != nullptr) && (split == 0);
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {

@@ -619,6 +619,39 @@ pm_bwd_kernel(const float* __restrict__ low, const long long* __restrict__ label
     }
 }
 
+// dense-tensor form (free function paed_loss_multiclass_soft on [B,C,S,S] mask / probability tensors)
+// mode 0: out = m - p ; mode 1: loss += pen*|t| (class penalty) or |t|, out = u ; mode 2: out = dp = a - bu
+__global__ void __launch_bounds__(256)
+pmd_elem_kernel(const float* __restrict__ m, const float* __restrict__ p, const float* __restrict__ t,
+                const float* __restrict__ bu, float* __restrict__ out, float* __restrict__ loss_sum, long long n,
+                int mode, int class_penalty) {
+  __shared__ float s_red[8];
+  float loss = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) {
+      out[i] = m[i] - p[i];
+    } else if (mode == 1) {
+      const float tv = t[i];
+      const float pen = class_penalty ? m[i] * (1.0f - p[i]) * 2.0f : 1.0f;
+      loss += pen * fabsf(tv);
+      out[i] = pen * (tv > 0.0f ? 1.0f : (tv < 0.0f ? -1.0f : 0.0f));
+    } else {
+      const float a = class_penalty ? -2.0f * m[i] * fabsf(t[i]) : 0.0f;
+      out[i] = a - bu[i];
+    }
+  }
+  if (mode == 1) {
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float l = 0.0f;
+      for (int i = 0; i < 8; ++i) l += s_red[i];
+      atomicAdd(loss_sum, l);
+    }
+  }
+}
+
 static int check_grid(const char* fn, int B, int C, int g, int S) {
   if (B <= 0 || C <= 0 || g <= 0 || S <= 0 || S % g != 0) { set_error("%s: bad shape B=%d C=%d g=%d S=%d", fn, B, C, g, S); return -1; }
   const int P = S / g;
@@ -780,4 +813,32 @@ extern "C" int vs_paed_multiclass(const float* low, const int64_t* labels, float
   if (C <= 4) return paed_multiclass_impl<4>(low, lab, t1, t2, t3, loss_sum, dlow, B, C, g, S, st);
   if (C <= 17) return paed_multiclass_impl<17>(low, lab, t1, t2, t3, loss_sum, dlow, B, C, g, S, st);
   return paed_multiclass_impl<32>(low, lab, t1, t2, t3, loss_sum, dlow, B, C, g, S, st);
+}
+
+extern "C" int vs_paed_multiclass_dense(const float* msk, const float* prob, float* t1, float* t2, float* t3,
+                                        float* loss_sum, float* dprob, int32_t B, int32_t C, int32_t S,
+                                        int32_t class_penalty, void* stream) {
+  VS_CHECK_ARG(msk && prob && t1 && t2 && loss_sum, "vs_paed_multiclass_dense: null pointer");
+  VS_CHECK_ARG(dprob == nullptr || t3 != nullptr, "vs_paed_multiclass_dense: t3 scratch required for the backward pass");
+  VS_CHECK_ARG(B > 0 && C > 0 && S > 0, "vs_paed_multiclass_dense: bad shape");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_paed_multiclass_dense: no CUDA device");
+  if (int rc = ensure_gauss()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long planes = (long long)B * C;
+  const long long n = planes * S * S;
+  long long bg = (n + 255) / 256;
+  if (bg > (long long)nsm * 32) bg = (long long)nsm * 32;
+  const unsigned grid = (unsigned)bg;
+  pmd_elem_kernel<<<grid, 256, 0, st>>>(msk, prob, nullptr, nullptr, t1, nullptr, n, 0, class_penalty);
+  blur1d_kernel<<<grid, 256, 0, st>>>(t1, t2, planes, S, 0);
+  blur1d_kernel<<<grid, 256, 0, st>>>(t2, t1, planes, S, 1);
+  pmd_elem_kernel<<<grid, 256, 0, st>>>(msk, prob, t1, nullptr, t2, loss_sum, n, 1, class_penalty);
+  if (dprob != nullptr) {
+    blur1d_kernel<<<grid, 256, 0, st>>>(t2, t3, planes, S, 0);
+    blur1d_kernel<<<grid, 256, 0, st>>>(t3, t2, planes, S, 1);
+    pmd_elem_kernel<<<grid, 256, 0, st>>>(msk, prob, t1, t2, dprob, nullptr, n, 2, class_penalty);
+  }
+  VS_CHECK_LAUNCH();
+  return 0;
 }

@@ -61,7 +61,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
     const long long t2 = row / gp;
     const int ty = int(t2 % gp), b = int(t2 / gp);
     const float4 v = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + c) * S + (ty * P + ph)) * S + tx * P + pw);
-    *reinterpret_cast<uint2*>(out + row * K + k) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    const long long orow = (long long)b * (gp * gp + 1) + 1 + ty * gp + tx;
+    *reinterpret_cast<uint2*>(out + orow * K + k) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
 }
 
@@ -74,8 +75,8 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 }
 
 // dpos[t, d] += sum_b dx[b, t, d]; dcls[d] += sum_b dx[b, 0, d]
-__global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos, int B,
-                                 int T1, int D) {
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
+                                 float* __restrict__ dbias, int B, int T1, int D) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over T1 * D/4
   const int D4 = D / 4;
   if (idx >= T1 * D4) return;
@@ -94,6 +95,9 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict
     float4 c = *dc;
     c.x += s.x; c.y += s.y; c.z += s.z; c.w += s.w;
     *dc = c;
+  } else {
+    float* db = dbias + (idx % D4) * 4;
+    atomicAdd(db + 0, s.x); atomicAdd(db + 1, s.y); atomicAdd(db + 2, s.z); atomicAdd(db + 3, s.w);
   }
 }
 
@@ -355,11 +359,12 @@ extern "C" int vs_cls_rows(const float* cls, const float* pos, float* x, int32_t
   return 0;
 }
 
-extern "C" int vs_embed_bwd(const float* dx, float* dcls, float* dpos, int32_t B, int32_t T1, int32_t D, void* stream) {
-  VS_CHECK_ARG(dx && dcls && dpos && B > 0 && T1 > 0 && D % 4 == 0, "vs_embed_bwd: bad arguments");
+extern "C" int vs_embed_bwd(const float* dx, float* dcls, float* dpos, float* dbias, int32_t B, int32_t T1, int32_t D,
+                            void* stream) {
+  VS_CHECK_ARG(dx && dcls && dpos && dbias && B > 0 && T1 > 0 && D % 4 == 0, "vs_embed_bwd: bad arguments");
   VS_CHECK_ARG(sm_count() > 0, "vs_embed_bwd: no CUDA device");
   const int total = T1 * (D / 4);
-  embed_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dx, dcls, dpos, B, T1, D);
+  embed_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dx, dcls, dpos, dbias, B, T1, D);
   VS_CHECK_LAUNCH();
   return 0;
 }

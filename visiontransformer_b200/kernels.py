@@ -111,8 +111,8 @@ def cls_rows(cls, pos, x, B, T1, D):
     check(_lib.load().vs_cls_rows(ptr(cls), ptr(pos), ptr(x), B, T1, D, stream()), "vs_cls_rows")
 
 
-def embed_bwd(dx, dcls, dpos, B, T1, D):
-    check(_lib.load().vs_embed_bwd(ptr(dx), ptr(dcls), ptr(dpos), B, T1, D, stream()), "vs_embed_bwd")
+def embed_bwd(dx, dcls, dpos, dbias, B, T1, D):
+    check(_lib.load().vs_embed_bwd(ptr(dx), ptr(dcls), ptr(dpos), ptr(dbias), B, T1, D, stream()), "vs_embed_bwd")
 
 
 def head_im2col(tokens, col, B, g, D):
@@ -192,6 +192,16 @@ def paed_multiclass(low, labels, t1, t2, t3, loss_sum, dlow):
     assert labels.dtype == torch.int64 and labels.is_contiguous() and low.is_contiguous()
     check(_lib.load().vs_paed_multiclass(ptr(low), ptr(labels), ptr(t1), ptr(t2), ptr(t3), ptr(loss_sum), ptr(dlow), B,
                                         Cn, g, S, stream()), "vs_paed_multiclass")
+
+
+def paed_multiclass_dense(msk, prob, t1, t2, t3, loss_sum, dprob, class_penalty=True):
+    require_cuda(prob, "paed_multiclass_dense")
+    B, Cn, S, S2 = prob.shape
+    assert S == S2 and msk.shape == prob.shape and msk.dtype == F32 and prob.dtype == F32
+    assert msk.is_contiguous() and prob.is_contiguous()
+    check(_lib.load().vs_paed_multiclass_dense(ptr(msk), ptr(prob), ptr(t1), ptr(t2), ptr(t3), ptr(loss_sum),
+                                              ptr(dprob), B, Cn, S, int(class_penalty), stream()),
+          "vs_paed_multiclass_dense")
 
 
 def cast_bf16(src, dst):

@@ -1,0 +1,143 @@
+"""Drop-in for the reference's model/PAED/classes.py live code:
+   paed_loss_multiclass_soft (:336-369), LightningViTModel (:415-487, multi-class soft PAED loss),
+   PAEDTrainer (:490-701, BCE + 0.1 Dice + 5 |PAED| on a 1-channel model).
+Dead / string-quoted code of the reference is intentionally not reproduced."""
+import torch
+import torch.nn.functional as F
+from torch.optim import AdamW
+from torch.optim.lr_scheduler import ReduceLROnPlateau
+
+from .. import kernels as K
+from .._lightning import LightningModule
+from ..losses import paed_binary_loss, paed_multiclass_soft_fused
+from ..model import ViTSegmentationModel
+from . import segmentation
+
+__all__ = ["ViTSegmentationModel", "LightningViTModel", "PAEDTrainer", "paed_loss_multiclass_soft"]
+
+
+def paed_loss_multiclass_soft(msk, pred_mask, num_classes=17, sigma=3, class_penalty=True):
+    """Dense-tensor form of model/PAED/classes.py:336-369 for callers that already hold [B,C,H,W] mask and
+    probability tensors.  The training wrappers below use the fused low-resolution path instead."""
+    from ..losses import paed_multiclass_dense
+    return paed_multiclass_dense(msk, pred_mask, sigma=sigma, class_penalty=class_penalty)
+
+
+class LightningViTModel(LightningModule):
+    def __init__(self, num_classes, patch_size, hidden_size, num_hidden_layers, num_attention_heads, **kwargs):
+        super().__init__()
+        num_classes = 17  # model/PAED/classes.py:418 forces 17 classes
+        self.num_classes = num_classes
+        self.model = ViTSegmentationModel(num_classes, patch_size, hidden_size, num_hidden_layers,
+                                          num_attention_heads, **kwargs)
+
+    def forward(self, x):
+        return self.model(x)
+
+    def _resize_target(self, y, size):
+        return F.interpolate(y.unsqueeze(1).float(), size=size, mode='nearest').squeeze(1).long()
+
+    def iou_score(self, preds, targets, num_classes=17):
+        # model/PAED/classes.py:430-447: mean over classes of the batch-mean per-image IoU (monitoring only)
+        ious = []
+        for c in range(num_classes):
+            p, t = (preds == c), (targets == c)
+            inter = (p & t).flatten(1).sum(1).float()
+            union = (p | t).flatten(1).sum(1).float()
+            ious.append(((inter + 1e-6) / (union + 1e-6)).mean())
+        return torch.stack(ious).mean()
+
+    def _step(self, batch):
+        x, y = batch
+        S = x.shape[-1]
+        y = self._resize_target(y, size=(S, S)).long()
+        low = self.model.forward_lowres(x)
+        loss = paed_multiclass_soft_fused(low, y, S)
+        with torch.no_grad():
+            preds = K.upsample_argmax(low.detach(), torch.empty(x.shape[0], S, S, device=x.device, dtype=torch.uint8))
+            iou = self.iou_score(preds.long(), y, self.num_classes)
+        return loss, iou
+
+    def training_step(self, batch, batch_idx):
+        loss, iou = self._step(batch)
+        self.log("train_loss", loss, prog_bar=True, on_epoch=True, logger=True)
+        self.log("train_iou", iou, prog_bar=True, on_epoch=True, logger=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        loss, iou = self._step(batch)
+        self.log("valid_loss", loss, prog_bar=True, on_epoch=True, logger=True)
+        self.log("valid_iou", iou, prog_bar=True, on_epoch=True, logger=True)
+        return loss
+
+    def configure_optimizers(self):
+        return torch.optim.Adam(self.parameters(), lr=1e-4)
+
+
+class PAEDTrainer(LightningModule):
+    def __init__(self, num_classes, patch_size, hidden_size, num_hidden_layers, num_attention_heads, **kwargs):
+        super().__init__()
+        self.model = ViTSegmentationModel(num_classes, patch_size, hidden_size, num_hidden_layers,
+                                          num_attention_heads, **kwargs)
+        # set by the data-parallel wrapper: global-batch Dice / |PAED| need cross-rank sums
+        self.dp_group = None
+        self.dp_world_size = 1
+
+    def _resize_target(self, y, size=(224, 224)):
+        if y.dim() == 3:
+            y = y.unsqueeze(1)
+        elif y.dim() == 4 and y.shape[1] != 1:
+            raise ValueError(f"Expected single-channel mask but got shape {y.shape}")
+        return F.interpolate(y.float(), size=size, mode='nearest').squeeze(1).long()
+
+    def forward(self, x):
+        return self.model(x)
+
+    def dice_loss(self, preds, targets, smooth=1e-6):
+        raise RuntimeError("PAEDTrainer.dice_loss is fused into the PAED-binary loss kernels; use "
+                           "visiontransformer_b200.losses.paed_binary_loss")
+
+    def _forward_step(self, batch, batch_idx):
+        return self._forward_step_paed(batch, batch_idx)
+
+    def _forward_step_paed(self, batch, batch_idx):
+        images, masks, sdf_ext, sdf_int = batch
+        S = images.shape[-1]
+        masks = self._resize_target(masks, size=(S, S))
+        if sdf_ext.shape[-1] != S or sdf_ext.shape[-2] != S:
+            # model/PAED/classes.py:635-636 (identity when the SDFs already are SxS, as produced by the dataset)
+            sdf_ext = F.interpolate(sdf_ext.unsqueeze(1), size=(S, S), mode='bilinear', align_corners=False).squeeze(1)
+            sdf_int = F.interpolate(sdf_int.unsqueeze(1), size=(S, S), mode='bilinear', align_corners=False).squeeze(1)
+        low = self.model.forward_lowres(images)
+        loss = paed_binary_loss(low, masks.float(), sdf_ext, sdf_int, S, group=self.dp_group,
+                                world_size=self.dp_world_size)
+        with torch.no_grad():
+            bin_preds = K.upsample_argmax(low.detach(), torch.empty(images.shape[0], S, S, device=images.device,
+                                                                    dtype=torch.uint8)).int()
+            m = masks.int()
+            acc = segmentation.pixel_accuracy(m, bin_preds)
+            iou = segmentation.intersection_over_union(m, bin_preds)
+            dice = segmentation.dice_score(m, bin_preds)
+            tp = (bin_preds & m).sum().float()
+            prec = tp / bin_preds.sum().float().clamp_min(1.0)
+            rec = tp / m.sum().float().clamp_min(1.0)
+        self.log_dict({"train_loss": loss, "train_acc": acc, "train_IoU": iou, "train_dice": dice,
+                       "train_precision": prec, "train_recall": rec}, on_epoch=True)
+        return loss, acc, iou, dice, prec, rec
+
+    def training_step(self, batch, batch_idx):
+        loss, accuracy, iou, dice, precision, recall = self._forward_step(batch, batch_idx)
+        self.log_dict({"train_loss": loss}, on_epoch=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        loss, accuracy, iou, dice, precision, recall = self._forward_step(batch, batch_idx)
+        self.log_dict({"val_loss": loss, "val_acc": accuracy, "val_IoU": iou, "val_recall": recall, "val_dice": dice,
+                       "val_precision": precision}, on_epoch=True)
+        return loss
+
+    def configure_optimizers(self):
+        optimizer = AdamW(self.model.parameters(), lr=1e-4)
+        scheduler = ReduceLROnPlateau(optimizer, patience=30)
+        return {"optimizer": optimizer,
+                "lr_scheduler": {"scheduler": scheduler, "monitor": "val_IoU", "interval": "epoch", "frequency": 1}}
