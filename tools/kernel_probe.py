@@ -109,17 +109,15 @@ def probe_gemm():
     case(12608, 3072, 768, False, False, bias=True, act=1)
 
     def patch_case():
-        Bn, T, D, Kd = 3, 196, 768, 768
-        a = bf(torch.randn(Bn * T, Kd, device=dev))
+        Bn, T1, D, Kd = 3, 197, 768, 768
+        a = bf(torch.randn(Bn * T1, Kd, device=dev))
         w = bf(torch.randn(D, Kd, device=dev) * 0.1)
         bias = torch.randn(D, device=dev)
-        pos = torch.randn(T + 1, D, device=dev)
-        x = torch.zeros(Bn * (T + 1), D, device=dev)
-        K.gemm(a, w, x, bias=bias, residual=pos, row_tokens=T)
-        ref = (a.float() @ w.float().t() + bias).view(Bn, T, D) + pos[1:]
-        got = x.view(Bn, T + 1, D)[:, 1:]
-        report("gemm patch-embed row remap", rel(got, ref), 1e-2)
-        report("   cls rows untouched", x.view(Bn, T + 1, D)[:, 0].abs().max().item(), 0.0)
+        pos = torch.randn(T1, D, device=dev)
+        x = torch.zeros(Bn * T1, D, device=dev)
+        K.gemm(a, w, x, bias=bias, residual=pos, row_tokens=T1)
+        ref = (a.float() @ w.float().t() + bias).view(Bn, T1, D) + pos
+        report("gemm patch-embed broadcast residual (row % T1)", rel(x.view(Bn, T1, D), ref), 1e-2)
     run("gemm patch", patch_case)
 
 

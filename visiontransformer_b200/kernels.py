@@ -16,6 +16,42 @@ ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 AUX_NONE, AUX_GELU_GRAD, AUX_RELU_MASK = 0, 1, 2
 
 
+# --- bookkeeping used by bench.py: kernels launched by this process and CUDA-event timing of the GEMM kernel -------
+_LAUNCHES = 0
+_GEMM_TIMING = False
+_GEMM_EVENTS = []
+
+
+def _count(n: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def reset_launch_count() -> None:
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def enable_gemm_timing(flag: bool) -> None:
+    """Bracket every vs_gemm_bf16 launch with CUDA events on the launching stream (bench.py roofline)."""
+    global _GEMM_TIMING
+    _GEMM_TIMING = flag
+    if flag:
+        _GEMM_EVENTS.clear()
+
+
+def collect_gemm_timing():
+    """-> list of (algorithmic FLOPs, milliseconds) per GEMM launch recorded since enable_gemm_timing(True)."""
+    torch.cuda.synchronize()
+    out = [(fl, e0.elapsed_time(e1)) for fl, e0, e1 in _GEMM_EVENTS]
+    _GEMM_EVENTS.clear()
+    return out
+
+
 def _rowmajor(t: torch.Tensor, what: str) -> int:
     assert t.dim() == 2 and t.stride(1) == 1, f"{what}: expected a row-major 2-D view, got strides {t.stride()}"
     return t.stride(0)
@@ -59,13 +95,22 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=Non
         d.residual, d.ldr = ptr(residual), _rowmajor(residual, "residual")
     d.row_tokens = row_tokens
     d.split_k = split_k
-    check(_lib.load().vs_gemm_bf16(C.byref(d), stream()), "vs_gemm_bf16")
+    if _GEMM_TIMING:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.load().vs_gemm_bf16(C.byref(d), stream()), "vs_gemm_bf16")
+        e1.record()
+        _GEMM_EVENTS.append((2.0 * M * N * K, e0, e1))
+    else:
+        check(_lib.load().vs_gemm_bf16(C.byref(d), stream()), "vs_gemm_bf16")
+    _count(1)
     return out
 
 
 def colsum(x, out, accumulate=True):
     require_cuda(x, "colsum")
     assert x.dtype == BF16 and out.dtype == F32
+    _count(1)
     check(_lib.load().vs_colsum_bf16(ptr(x), _rowmajor(x, "x"), x.shape[0], x.shape[1], ptr(out), int(accumulate),
                                     stream()), "vs_colsum_bf16")
     return out
@@ -75,6 +120,7 @@ def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=
     require_cuda(x, "layernorm_fwd")
     assert x.dtype == F32 and x.is_contiguous()
     M, D = x.shape
+    _count(1)
     check(_lib.load().vs_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), eps, M, D, ptr(y_bf16), ptr(y_f32), ptr(mean),
                                       ptr(rstd), stream()), "vs_layernorm_fwd")
 
@@ -83,6 +129,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_bf16, dgamma, dbet
     require_cuda(x, "layernorm_bwd")
     M, D = x.shape
     assert dy.is_contiguous() and dy.dtype in (BF16, F32)
+    _count(1)
     check(_lib.load().vs_layernorm_bwd(ptr(dy), int(dy.dtype == F32), ptr(x), ptr(gamma), ptr(mean), ptr(rstd),
                                       ptr(dx_in), M, D, ptr(dx_out), ptr(dx_bf16), ptr(dgamma), ptr(dbeta), stream()),
           "vs_layernorm_bwd")
@@ -91,11 +138,13 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_bf16, dgamma, dbet
 def attention_fwd(qkv, ctx, lse, B, N, H, scale):
     require_cuda(qkv, "attention_fwd")
     assert qkv.dtype == BF16 and qkv.is_contiguous() and ctx.is_contiguous()
+    _count(1)
     check(_lib.load().vs_attention_fwd(ptr(qkv), ptr(ctx), ptr(lse), B, N, H, scale, stream()), "vs_attention_fwd")
 
 
 def attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_accum, delta, B, N, H, scale):
     require_cuda(qkv, "attention_bwd")
+    _count(2)
     check(_lib.load().vs_attention_bwd(ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse), ptr(dqkv), ptr(dq_accum), ptr(delta), B,
                                       N, H, scale, stream()), "vs_attention_bwd")
 
@@ -104,30 +153,37 @@ def patchify(img, out, P):
     require_cuda(img, "patchify")
     assert img.dtype == F32 and img.is_contiguous()
     B, _, S, _ = img.shape
+    _count(1)
     check(_lib.load().vs_patchify(ptr(img), ptr(out), B, S, P, stream()), "vs_patchify")
 
 
 def cls_rows(cls, pos, x, B, T1, D):
+    _count(1)
     check(_lib.load().vs_cls_rows(ptr(cls), ptr(pos), ptr(x), B, T1, D, stream()), "vs_cls_rows")
 
 
 def embed_bwd(dx, dcls, dpos, dbias, B, T1, D):
+    _count(1)
     check(_lib.load().vs_embed_bwd(ptr(dx), ptr(dcls), ptr(dpos), ptr(dbias), B, T1, D, stream()), "vs_embed_bwd")
 
 
 def head_im2col(tokens, col, B, g, D):
+    _count(1)
     check(_lib.load().vs_head_im2col(ptr(tokens), ptr(col), B, g, D, stream()), "vs_head_im2col")
 
 
 def head_col2im(dcol, dtokens, B, g, D):
+    _count(1)
     check(_lib.load().vs_head_col2im(ptr(dcol), ptr(dtokens), B, g, D, stream()), "vs_head_col2im")
 
 
 def conv1x1_fwd(feat, w, b, logits, B, g, F, Cn):
+    _count(1)
     check(_lib.load().vs_conv1x1_fwd(ptr(feat), ptr(w), ptr(b), ptr(logits), B, g, F, Cn, stream()), "vs_conv1x1_fwd")
 
 
 def conv1x1_bwd(dlogits, feat, w, dfeat, dw, db, B, g, F, Cn):
+    _count(1)
     check(_lib.load().vs_conv1x1_bwd(ptr(dlogits), ptr(feat), ptr(w), ptr(dfeat), ptr(dw), ptr(db), B, g, F, Cn,
                                     stream()), "vs_conv1x1_bwd")
 
@@ -137,6 +193,7 @@ def upsample_fwd(low, full):
     B, Cn, g, _ = low.shape
     S = full.shape[-1]
     assert low.is_contiguous() and full.is_contiguous() and low.dtype == F32 and full.dtype == F32
+    _count(1)
     check(_lib.load().vs_upsample_bilinear_fwd(ptr(low), ptr(full), B, Cn, g, S, stream()), "vs_upsample_bilinear_fwd")
     return full
 
@@ -145,6 +202,7 @@ def upsample_bwd(dfull, dlow):
     B, Cn, g, _ = dlow.shape
     S = dfull.shape[-1]
     assert dfull.is_contiguous() and dfull.dtype == F32
+    _count(1)
     check(_lib.load().vs_upsample_bilinear_bwd(ptr(dfull), ptr(dlow), B, Cn, g, S, stream()), "vs_upsample_bilinear_bwd")
     return dlow
 
@@ -154,6 +212,7 @@ def upsample_argmax(low, mask):
     B, Cn, g, _ = low.shape
     S = mask.shape[-1]
     assert mask.dtype == torch.uint8 and mask.is_contiguous() and low.is_contiguous()
+    _count(1)
     check(_lib.load().vs_upsample_argmax(ptr(low), ptr(mask), B, Cn, g, S, stream()), "vs_upsample_argmax")
     return mask
 
@@ -163,6 +222,7 @@ def upsample_ce(low, labels, loss_sum, dlow):
     B, Cn, g, _ = low.shape
     S = labels.shape[-1]
     assert labels.dtype == torch.int64 and labels.is_contiguous() and low.is_contiguous()
+    _count(1)
     check(_lib.load().vs_upsample_ce(ptr(low), ptr(labels), ptr(loss_sum), ptr(dlow), B, Cn, g, S, stream()),
           "vs_upsample_ce")
 
@@ -173,6 +233,7 @@ def paed_binary_stats(low, mask, sdf_ext, sdf_int, stats, keys):
     S = mask.shape[-1]
     for t in (low, mask, sdf_ext, sdf_int):
         assert t.dtype == F32 and t.is_contiguous()
+    _count(1)
     check(_lib.load().vs_paed_binary_stats(ptr(low), ptr(mask), ptr(sdf_ext), ptr(sdf_int), ptr(stats), ptr(keys), B, g,
                                           S, stream()), "vs_paed_binary_stats")
 
@@ -181,6 +242,7 @@ def paed_binary_bwd(low, mask, sdf_ext, sdf_int, coef, keys, dlow):
     B, _, g, _ = low.shape
     S = mask.shape[-1]
     assert coef.dtype == F32 and coef.is_contiguous()
+    _count(1)
     check(_lib.load().vs_paed_binary_bwd(ptr(low), ptr(mask), ptr(sdf_ext), ptr(sdf_int), ptr(coef), ptr(keys),
                                         ptr(dlow), B, g, S, stream()), "vs_paed_binary_bwd")
 
@@ -190,6 +252,7 @@ def paed_multiclass(low, labels, t1, t2, t3, loss_sum, dlow):
     B, Cn, g, _ = low.shape
     S = labels.shape[-1]
     assert labels.dtype == torch.int64 and labels.is_contiguous() and low.is_contiguous()
+    _count(7 if dlow is not None else 4)
     check(_lib.load().vs_paed_multiclass(ptr(low), ptr(labels), ptr(t1), ptr(t2), ptr(t3), ptr(loss_sum), ptr(dlow), B,
                                         Cn, g, S, stream()), "vs_paed_multiclass")
 
@@ -199,6 +262,7 @@ def paed_multiclass_dense(msk, prob, t1, t2, t3, loss_sum, dprob, class_penalty=
     B, Cn, S, S2 = prob.shape
     assert S == S2 and msk.shape == prob.shape and msk.dtype == F32 and prob.dtype == F32
     assert msk.is_contiguous() and prob.is_contiguous()
+    _count(7 if dprob is not None else 4)
     check(_lib.load().vs_paed_multiclass_dense(ptr(msk), ptr(prob), ptr(t1), ptr(t2), ptr(t3), ptr(loss_sum),
                                               ptr(dprob), B, Cn, S, int(class_penalty), stream()),
           "vs_paed_multiclass_dense")
@@ -207,11 +271,13 @@ def paed_multiclass_dense(msk, prob, t1, t2, t3, loss_sum, dprob, class_penalty=
 def cast_bf16(src, dst):
     require_cuda(src, "cast_bf16")
     assert src.dtype == F32 and dst.dtype == BF16 and src.is_contiguous() and dst.is_contiguous()
+    _count(1)
     check(_lib.load().vs_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream()), "vs_cast_f32_bf16")
 
 
 def cast_bf16_rows(src, dst):
     M, D = src.shape
+    _count(1)
     check(_lib.load().vs_cast_bf16_rows(ptr(src), _rowmajor(src, "src"), ptr(dst), _rowmajor(dst, "dst"), M, D,
                                        stream()), "vs_cast_bf16_rows")
 
@@ -219,9 +285,11 @@ def cast_bf16_rows(src, dst):
 def pack_conv3x3(w, out):
     O, I = w.shape[0], w.shape[1]
     assert w.is_contiguous()
+    _count(1)
     check(_lib.load().vs_pack_conv3x3(ptr(w), ptr(out), O, I, stream()), "vs_pack_conv3x3")
 
 
 def unpack_conv3x3_grad(g, dw):
     O, I = dw.shape[0], dw.shape[1]
+    _count(1)
     check(_lib.load().vs_unpack_conv3x3_grad(ptr(g), ptr(dw), O, I, stream()), "vs_unpack_conv3x3_grad")
