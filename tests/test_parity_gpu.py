@@ -175,8 +175,11 @@ def test_vitb16_logits_and_argmax_vs_golden(golden_dir):
     conf_agree = (full.argmax(1).cpu() == ref_arg)[confident].float().mean().item()
     print(f"vitb16: logits err {err:.2e}, raw argmax agreement {raw:.5f}, margin-filtered {conf_agree:.5f} "
           f"({confident.float().mean().item():.3f} of pixels)")
+    # random-init logits are nearly flat (top-2 margins down to 1e-4), so raw agreement is bounded by near-ties
+    # (even fp32-vs-bf16-weights alone gives 99.4-99.9 %); the 99.9 % bar is asserted on pixels whose
+    # fp32 margin exceeds twice the measured logit error, and on trained weights in test_ce_loss_curve_tracks_oracle.
     assert conf_agree >= 0.999
-    assert raw >= 0.999
+    assert raw >= 0.995
     # fused upsample+argmax equals argmax of the materialised logits
     assert (mask.cpu().long() == full.argmax(1).cpu()).float().mean().item() > 0.9999
     y = m._resize_target(O.synthetic_labels(2, 17, seed=gold["label_seed"]).to(dev), (224, 224))
@@ -248,6 +251,18 @@ def test_ce_loss_curve_tracks_oracle():
     print(f"loss curve: oracle {first:.4f} -> {last:.4f}; worst relative gap {worst:.3e}")
     assert last < 0.9 * first, "the synthetic task should be learnable"
     assert worst < 1e-2
+    # argmax-mask agreement on TRAINED weights (margins O(1)): the candidate's weights evaluated by both paths
+    m.eval()
+    trained = {k[len("model."):]: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    xe = O.synthetic_images(4, 224, seed=33)
+    with torch.no_grad():
+        ours = m(xe.to(dev)).argmax(1).cpu()
+        mask = m.model.predict_mask(xe.to(dev)).cpu().long()
+        ref = O.forward(trained, xe, cfg).argmax(1)
+    agree = (ours == ref).float().mean().item()
+    print(f"trained-weights argmax agreement {agree:.5f}")
+    assert agree >= 0.999
+    assert (mask == ours).float().mean().item() >= 0.9999
 
 
 def test_gradient_accumulation_matches_single_batch():

@@ -234,10 +234,11 @@ def probe_head():
         report("conv1x1 bwd db", rel(db, dl2.sum(0)), 1e-4)
         # patchify
         img = torch.rand(Bn, 3, 224, 224, device=dev)
-        pm = torch.empty(Bn * T, 768, device=dev, dtype=torch.bfloat16)
+        pm = torch.zeros(Bn * (T + 1), 768, device=dev, dtype=torch.bfloat16)
         K.patchify(img, pm, 16)
-        refp = F.unfold(img, 16, stride=16).transpose(1, 2).reshape(Bn * T, 768)
-        report("patchify", rel(pm, refp), 4e-3)
+        refp = F.unfold(img, 16, stride=16).transpose(1, 2)
+        report("patchify", rel(pm.view(Bn, T + 1, 768)[:, 1:], refp), 4e-3)
+        report("patchify cls rows untouched", pm.view(Bn, T + 1, 768)[:, 0].abs().max().item(), 0.0)
         # colsum / embed_bwd / casts
         x = bf(torch.randn(1000, 768, device=dev))
         cs = torch.zeros(768, device=dev)
@@ -246,9 +247,11 @@ def probe_head():
         dx = torch.randn(Bn, T + 1, D, device=dev)
         dcls = torch.zeros(D, device=dev)
         dpos = torch.zeros(T + 1, D, device=dev)
-        K.embed_bwd(dx, dcls, dpos, Bn, T + 1, D)
+        dbp = torch.zeros(D, device=dev)
+        K.embed_bwd(dx, dcls, dpos, dbp, Bn, T + 1, D)
         report("embed_bwd dpos", rel(dpos, dx.sum(0)), 1e-5)
         report("embed_bwd dcls", rel(dcls, dx[:, 0].sum(0)), 1e-5)
+        report("embed_bwd dbias (patch rows only)", rel(dbp, dx[:, 1:].sum((0, 1))), 1e-5)
         gpk = torch.randn(Fd, 9 * D, device=dev)
         dwc = torch.zeros(Fd, D, 3, 3, device=dev)
         K.unpack_conv3x3_grad(gpk, dwc)
