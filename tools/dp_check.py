@@ -61,9 +61,11 @@ def compare(tag, cls, C, batch, make_opt, steps=3):
 B = 4 * world
 x = O.synthetic_images(B, 224, seed=1).to(dev)
 y = O.synthetic_labels(B, 17, seed=2).to(dev)
-compare("CE", LightningViTModel, 17, (x, y), lambda m: torch.optim.Adam(m.parameters(), lr=1e-3))
+# plain SGD: Adam's g/sqrt(v) turns bf16-level gradient noise on near-zero gradients into O(lr) weight differences,
+# which says nothing about the all-reduce; SGD keeps the comparison linear in the gradients.
+compare("CE", LightningViTModel, 17, (x, y), lambda m: torch.optim.SGD(m.parameters(), lr=0.05))
 masks, se, si = [t.to(dev) for t in O.synthetic_binary_targets(B, 224, seed=3)]
-compare("PAEDTrainer", PAEDTrainer, 1, (x, masks, se, si), lambda m: torch.optim.AdamW(m.parameters(), lr=1e-3))
+compare("PAEDTrainer", PAEDTrainer, 1, (x, masks, se, si), lambda m: torch.optim.SGD(m.parameters(), lr=0.05))
 # sharded inference: gathered masks == single-process masks
 m = build(LightningViTModel, 17, 5).eval()
 dp = DataParallel(m)
