@@ -177,7 +177,8 @@ def run_ours(args):
     torch.manual_seed(0)
     lm = LightningViTModel(**MODEL, image_size=IMAGE, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     lm = lm.to(dev).train()
-    opt = torch.optim.Adam(lm.parameters(), lr=1e-5, fused=True)   # model/CE/classes.py:296-297
+    # model/CE/classes.py:296-297; capturable so that the whole step can live in one CUDA graph
+    opt = torch.optim.Adam(lm.parameters(), lr=1e-5, fused=True, capturable=True)
     dp = DataParallel(lm, opt)
     dp.broadcast_parameters()
 
@@ -207,22 +208,33 @@ def run_ours(args):
             ms = t.item()
         return ms
 
+    # ---- the whole step (fwd + fused loss + bwd + bucketed all-reduce + Adam) as ONE CUDA graph
+    from visiontransformer_b200.graph import GraphedTrainStep
+    for i in range(2):
+        dp.step((dx, dy), i)           # eager warm-up (one-time attribute sets, arena build)
+    K.reset_launch_count()
+    dp.step((dx, dy), 0)
+    launches_per_step = K.launch_count()   # libvitseg kernels per step (torch's Adam / label-resize kernels not counted)
+    if args.no_graph:
+        graphed = None
+    else:
+        graphed = GraphedTrainStep(lambda b, i: dp.step(b, i), (dx, dy), warmup=2, engines=[lm.model.engine])
+
     def resident_step(i):
-        dp.step((dx, dy), i)
+        if graphed is None:
+            dp.step((dx, dy), i)
+        else:
+            graphed.replay()
 
     # ---- warm-up, then `value`
     for i in range(max(3, args.warmup)):
         resident_step(i)
-    K.reset_launch_count()
-    K.enable_gemm_timing(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(resident_step, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
-    gemm_events = K.collect_gemm_timing()
-    K.enable_gemm_timing(False)
-    launches = K.launch_count()
+    launches = launches_per_step * args.steps
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- e2e: pinned host batches, prefetched on a copy stream one step ahead, loss read back every step
@@ -246,7 +258,10 @@ def run_ours(args):
             prefetch(0)
         prefetch(slot ^ 1)  # next step's batch overlaps this step's compute
         torch.cuda.current_stream().wait_event(ready[slot])
-        loss = dp.step((dev_x[slot], dev_y[slot]), i)
+        if graphed is None:
+            loss = dp.step((dev_x[slot], dev_y[slot]), i)
+        else:
+            loss = graphed((dev_x[slot], dev_y[slot]))   # D2D into the graph's static inputs, then replay
         consumed[slot].record()
         losses.append(loss.item())  # device -> host read of the step result
 
@@ -257,6 +272,16 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
+
+    # ---- GEMM-kernel timing: the same step run eagerly with CUDA events around every vs_gemm_bf16 launch
+    # (events cannot be timed inside a captured graph; same kernels, same shapes, same stream)
+    K.enable_gemm_timing(True)
+    barrier()
+    for i in range(3):
+        dp.step((dx, dy), i)
+    gemm_events = K.collect_gemm_timing()
+    K.enable_gemm_timing(False)
+    ms_gemm_steps = None
 
     # ---- inference companions (same model): logits contract and fused mask path
     lm.eval()
@@ -279,8 +304,8 @@ def run_ours(args):
     if tot_ms > 0:
         ach = tot_flops / (tot_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "vs::gemm_kernel (tcgen05, all variants)", "launches_timed": len(gemm_events),
-                "share_of_step": tot_ms / ms, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"}
+                "traffic": None, "kernel": "vs::gemm_kernel (tcgen05, all variants)", "launches_timed": len(gemm_events), "timing": "CUDA events around each GEMM launch in 3 eager (non-graph) steps of the same workload",
+                "share_of_step": (tot_ms / 3) / (ms / args.steps), "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"}
     step_tflops = value * fl_img / 1e12
 
     if rank == 0:
@@ -295,7 +320,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "ViT-B/16 CE segmentation training, batch 64/GPU, 224x224, C=17 (BASELINE configs[1])",
-                       "global_batch": B * world, "parallelism": f"dp{world}", "optimizer": "Adam(lr=1e-5, fused) in timed region",
+                       "global_batch": B * world, "parallelism": f"dp{world}", "optimizer": "Adam(lr=1e-5, fused, capturable) in timed region", "cuda_graph": graphed is not None,
                        "dropout": 0.0, "l2": "working set (4.2 GB activations + 0.9 GB weights/grads per step) >> 126 MB L2; no flush needed",
                        "label_resize": "256->224 nearest inside the step, as LightningViTModel.training_step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -323,6 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,53 @@
+"""Whole-step CUDA graph: forward + loss + backward (+ gradient all-reduce) + optimizer step captured once and
+replayed, so the ~330 kernel launches of a ViT-B/16 training step cost one host call.
+
+Replaces the reference's host loop (Lightning automatic optimisation around training_step,
+model/CE/createViTmodel.py:68-77), whose per-module Python overhead is comparable to a B200 step.
+Every libvitseg entry point is capture-safe (no allocation, no host sync, stream-ordered memsets only)."""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+
+
+class GraphedTrainStep:
+    """step_fn(batch, idx) -> loss tensor must run the full optimisation step (e.g. DataParallel.step or a closure
+    doing training_step / backward / optimizer.step / zero_grad) using only the tensors of `batch`.
+
+    The optimizer must be capture-safe (torch.optim.Adam/AdamW(..., fused=True, capturable=True))."""
+
+    def __init__(self, step_fn: Callable, example_batch: Sequence[torch.Tensor], warmup: int = 3, engines=()):
+        self.step_fn = step_fn
+        self.engines = tuple(engines)  # their bf16 weight shadows are one optimizer step behind after a replay
+        self.static_batch = tuple(t.clone() for t in example_batch)
+        dev = self.static_batch[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(warmup):
+                self.step_fn(self.static_batch, i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.static_loss = self.step_fn(self.static_batch, 0)
+        self.steps = 0
+
+    def load(self, batch: Sequence[torch.Tensor], non_blocking: bool = True) -> None:
+        """copies a (host or device) batch into the graph's static input tensors on the current stream."""
+        for s, t in zip(self.static_batch, batch):
+            s.copy_(t, non_blocking=non_blocking)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        self.steps += 1
+        for eng in self.engines:
+            eng._versions = None  # force a re-cast of the weight shadows on the next eager forward
+        return self.static_loss
+
+    def __call__(self, batch: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        if batch is not None:
+            self.load(batch)
+        return self.replay()
