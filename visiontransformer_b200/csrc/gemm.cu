@@ -95,19 +95,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w / tiles;
-        const int t = w - split * tiles;
-        const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-        const int m0 = tm * BM, n0 = tn * BN;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.kblocks, kb0 + kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------ TMA producer (whole warp converged; one elected lane issues,
+    // so descriptors / coordinates stay in uniform registers)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w / tiles;
+      const int t = w - split * tiles;
+      const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      const int m0 = tm * BM, n0 = tn * BN;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(p.kblocks, kb0 + kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
@@ -126,29 +127,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int i = 0; i < BN / 64; ++i)
               tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w / tiles;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.kblocks, kb0 + kb_per_split);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ------------------------------------------------ MMA issuer (whole warp converged, elected lane issues:
+    // a divergent single-thread loop made ptxas wrap every UTCHMMA in ELECT/R2UR sequences and the issue loop,
+    // not the tensor pipe, became the limiter — ncu r01: tensor pipe 51 % active with the operands always ready)
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w / tiles;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(p.kblocks, kb0 + kb_per_split);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
           const uint64_t adesc = A_MN ? umma_desc_sw128(sa, BK * 128, 1024) : umma_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = B_MN ? umma_desc_sw128(sb, BK * 128, 1024) : umma_desc_sw128(sb, 16, 1024);
@@ -159,11 +164,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
