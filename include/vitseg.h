@@ -54,6 +54,8 @@ int vs_device_sm_count(void);
  * Broadcast residual (patch embedding + position embedding, TF:117-124): row_tokens = T1 > 0 reads residual row
  *   (m % T1), i.e. a [T1, N] table shared by every image; 0 = residual row m.
  * split_k: 0 = automatic (only >1 when accumulate != 0), else the number of K partitions.
+ * Tiling: CTA pairs (tcgen05 cta_group::2, 256 x {256,192,128} tiles) or single CTAs (128 x {256,128}), chosen by a
+ *   wave-quantisation cost model unless tile_cfg forces one.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct vs_gemm_desc {
   int32_t M, N, K;
@@ -77,6 +79,7 @@ typedef struct vs_gemm_desc {
   int64_t ldr;
   int32_t row_tokens;
   int32_t split_k;
+  int32_t tile_cfg; /* 0 = automatic; 1..5 force {pair 256xBN256, pair BN192, pair BN128, single-CTA BN256, BN128} */
 } vs_gemm_desc;
 
 int vs_gemm_bf16(const vs_gemm_desc* d, void* stream);

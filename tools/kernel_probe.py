@@ -83,7 +83,7 @@ def probe_gemm():
                 out.copy_(base)
                 ref = ref + base
             K.gemm(A, Bm, out, a_mn=a_mn, b_mn=b_mn, bias=bias, act=act, out2=out2, aux=aux, aux_mode=aux_mode,
-                   residual=res, accumulate=accumulate, split_k=kw.get("split_k", 0))
+                   residual=res, accumulate=accumulate, split_k=kw.get("split_k", 0), tile_cfg=kw.get("cfg", 0))
             torch.cuda.synchronize()
             report(f"gemm M{M} N{N} K{Kd} a_mn{int(a_mn)} b_mn{int(b_mn)} {kw}", rel(out, ref), 1e-2)
             if out2 is not None:
@@ -107,6 +107,13 @@ def probe_gemm():
     case(2304, 768, 4000, True, True, f32=True, acc=True, split_k=3)
     case(12608, 768, 768, False, False, bias=True)
     case(12608, 3072, 768, False, False, bias=True, act=1)
+    # every tile configuration x operand-major combination (cfg 1-3: cta_group::2 pairs; 4-5: single CTA)
+    for cfg in (1, 2, 3, 4, 5):
+        for a_mn in (False, True):
+            for b_mn in (False, True):
+                case(1000, 768, 832, a_mn, b_mn, f32=True, cfg=cfg)
+        case(12608, 768, 768, False, False, bias=True, res=True, f32=True, cfg=cfg)
+        case(768, 3072, 4000, True, True, f32=True, acc=True, split_k=2, cfg=cfg)
 
     def patch_case():
         Bn, T1, D, Kd = 3, 197, 768, 768

@@ -27,7 +27,7 @@ class GemmDesc(C.Structure):
         ("out2", c_void_p), ("ldo2", c_i64),
         ("aux", c_void_p), ("ldaux", c_i64), ("aux_mode", c_int),
         ("residual", c_void_p), ("ldr", c_i64),
-        ("row_tokens", c_int), ("split_k", c_int),
+        ("row_tokens", c_int), ("split_k", c_int), ("tile_cfg", c_int),
     ]
 
 

@@ -2,31 +2,34 @@
 //
 //   D[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
 //
-// One CTA per SM loops over (m-tile, n-tile, k-split) work items.  Roles:
-//   warp 0      : TMA producer  — streams 128xBK A tiles and BNxBK B tiles into a 4-stage 128B-swizzled smem ring
-//   warp 1      : MMA issuer    — one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into TMEM accumulators
-//   warp 2      : TMEM allocator (512 columns = two BN=256 fp32 accumulator stages)
-//   warps 4..11 : epilogue      — tcgen05.ld the accumulator (thread = output row), fused bias / GELU / ReLU /
-//                                 GELU' / residual / row-remap, bf16 or fp32 (or atomic fp32) stores
-// The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
-//
-// Both operands can be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the latter lets the
-// dgrad (dY·W) and wgrad (dYᵀ·X) GEMMs of the backward pass read the forward tensors in place, without transposes
-// (replaces autograd's mm_backward for TF:216-218,262,290,305).
+// Two flavours of one kernel template:
+//   CTA2 = 1 : CTA pairs (cluster 2x1) run tcgen05.mma.cta_group::2 on 256 x BN tiles.  Each CTA stages its own
+//              128 rows of A and HALF of the B tile; the pair's tensor cores share the B halves, which halves both
+//              the L2->SM operand traffic and the smem read bandwidth per MMA.  (ncu r01: the single-CTA M=128
+//              form tops out near 50 % tensor-pipe activity with operands always ready.)
+//   CTA2 = 0 : single-CTA 128 x BN tiles (cta_group::1) for problems too small to fill 74 pairs.
+// Roles per CTA (384 threads):
+//   warp 0      : TMA producer  — 128B-swizzled smem ring (6 x 32 KB stages for CTA2/BN=256), mbarrier completion
+//   warp 1      : MMA issuer    — leader CTA only; whole warp converged, one elected lane issues 4 UMMAs per stage
+//   warp 2      : TMEM allocator (512 columns = two fp32 accumulator stages)
+//   warps 4..11 : epilogue      — tcgen05.ld (thread = output row), fused bias / GELU / ReLU / GELU' / ReLU-mask /
+//                                 residual / bf16-or-fp32 / atomic-add stores; overlaps the next tile's MMAs
+// Operands can be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) so the dgrad (dY·W) and wgrad
+// (dYᵀ·X) GEMMs of the backward pass read forward tensors in place (replaces autograd's mm_backward for
+// TF:216-218,262,290,305).
 #include "common.cuh"
 #include "../../include/vitseg.h"
 
 namespace vs {
 
-constexpr int BM = 128;
+constexpr int BM = 128;  // rows of A per CTA
 constexpr int BK = 64;
-constexpr int kStages = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 
 struct GemmParams {
   int M, N, K;
-  int tiles_m, tiles_n, splits, kblocks;  // kblocks = ceil(K / BK)
+  int tiles_m, tiles_n, splits, kblocks;  // tiles_m counts (CTA2 ? 256 : 128)-row tiles; kblocks = ceil(K / BK)
   void* out;
   long long ldo;
   int out_f32, accumulate;
@@ -42,20 +45,157 @@ struct GemmParams {
   int row_tokens;
 };
 
-template <int BN>
-struct SmemLayout {
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+template <int BN, int CTA2>
+struct Cfg {
+  static constexpr int kBNH = CTA2 ? BN / 2 : BN;                // B rows staged per CTA
+  static constexpr int kBBoxes = (kBNH + 63) / 64;               // 64-wide MN-major boxes per CTA
+  static constexpr int kABytes = BM * BK * 2;                    // 16 KB
+  static constexpr int kBAlloc = kBBoxes * 64 * BK * 2;          // smem reserved for B per stage
+  static constexpr int kStageBytes = kABytes + kBAlloc;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static constexpr int kAccStride = 256;                         // TMEM columns between accumulator stages
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-template <int BN, int A_MN, int B_MN>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same-offset mbarrier of CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// pair-wide variants of the tcgen05 helpers
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t tmem_addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the same-offset mbarrier of BOTH CTAs of the pair once the issued MMAs retire
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue for one 32-row x 32-column chunk held as one row per thread
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&f)[32], int r, long long rrow, int n,
+                                               bool row_ok, bool first_split) {
+  if (p.bias != nullptr && first_split) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+    }
+  }
+  if (!row_ok) return;
+  const long long orow = r;
+  if (p.out2 != nullptr) {
+    uint4* o2 = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  }
+  if (p.aux_mode != 0) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + orow * p.ldaux + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 a = __ldg(a4 + j);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 x = unpack_bf16(aw[q]);
+        if (p.aux_mode == 1) {
+          f[8 * j + 2 * q] *= gelu_erf_grad(x.x);
+          f[8 * j + 2 * q + 1] *= gelu_erf_grad(x.y);
+        } else {
+          f[8 * j + 2 * q] = x.x > 0.0f ? f[8 * j + 2 * q] : 0.0f;
+          f[8 * j + 2 * q + 1] = x.y > 0.0f ? f[8 * j + 2 * q + 1] : 0.0f;
+        }
+      }
+    }
+  }
+  if (p.residual != nullptr && first_split) {
+    const float4* r4 = reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 x = r4[j];
+      f[4 * j + 0] += x.x; f[4 * j + 1] += x.y; f[4 * j + 2] += x.z; f[4 * j + 3] += x.w;
+    }
+  }
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
+    if (p.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(f[4 * j]),
+                     "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                     : "memory");
+    } else {
+      float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    }
+  } else {
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o4[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+  }
+}
+
+template <int BN, int A_MN, int B_MN, int CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
-  using L = SmemLayout<BN>;
+  using L = Cfg<BN, CTA2>;
+  constexpr int kStages = L::kStages;
+  constexpr int kNCta = CTA2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -66,7 +206,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kAccStages = (BN <= 256) ? 2 : 1;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   constexpr uint32_t kTmemCols = 512;
 
   if (warp == 0 && lane == 0) {
@@ -80,30 +221,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
+      mbar_init(&tempty_bar[i], kEpiWarps * kNCta);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc2(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles = p.tiles_m * p.tiles_n;
   const int total_work = tiles * p.splits;
   const int kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
+  const int unit = blockIdx.x / kNCta;
+  const int nunits = gridDim.x / kNCta;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer (whole warp converged; one elected lane issues,
-    // so descriptors / coordinates stay in uniform registers)
+    // ------------------------------------------------ TMA producer (each CTA loads its A rows and its B half)
+    constexpr uint32_t kBytesA = L::kABytes;
+    constexpr uint32_t kBytesB = B_MN ? L::kBBoxes * 64 * BK * 2 : L::kBNH * BK * 2;
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = unit; w < total_work; w += nunits) {
       const int split = w / tiles;
       const int t = w - split * tiles;
       const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-      const int m0 = tm * BM, n0 = tn * BN;
+      const int m0 = tm * (BM * kNCta) + rank * BM;
+      const int n0 = tn * BN + rank * L::kBNH;
       const int kb0 = split * kb_per_split;
       const int kb1 = min(p.kblocks, kb0 + kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -111,21 +260,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (elect_one()) {
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (leader) mbar_expect_tx(&full_bar[stage], (kBytesA + kBytesB) * kNCta);
           const int k0 = kb * BK;
           if (A_MN == 0) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+            if (CTA2) tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], k0, m0);
+            else tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m0 + i * 64, k0);
+            for (int i = 0; i < BM / 64; ++i) {
+              if (CTA2) tma_load_2d_2cta(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m0 + i * 64, k0);
+              else tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m0 + i * 64, k0);
+            }
           }
           if (B_MN == 0) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+            if (CTA2) tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], k0, n0);
+            else tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
+            for (int i = 0; i < L::kBBoxes; ++i) {
+              if (CTA2) tma_load_2d_2cta(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
+              else tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
+            }
           }
         }
         __syncwarp();
@@ -133,170 +288,167 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (whole warp converged, elected lane issues:
-    // a divergent single-thread loop made ptxas wrap every UTCHMMA in ELECT/R2UR sequences and the issue loop,
-    // not the tensor pipe, became the limiter — ncu r01: tensor pipe 51 % active with the operands always ready)
-    const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-    const uint32_t smem_base = smem_u32(smem);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int split = w / tiles;
-      const int kb0 = split * kb_per_split;
-      const int kb1 = min(p.kblocks, kb0 + kb_per_split);
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ------------------------------------------------ MMA issuer (leader CTA of the pair only)
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16(BM * kNCta, BN, A_MN, B_MN);
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = unit; w < total_work; w += nunits) {
+        const int split = w / tiles;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_base + stage * L::kStageBytes;
-          const uint32_t sb = sa + L::kABytes;
-          const uint64_t adesc = A_MN ? umma_desc_sw128(sa, BK * 128, 1024) : umma_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = B_MN ? umma_desc_sw128(sb, BK * 128, 1024) : umma_desc_sw128(sb, 16, 1024);
+        const uint32_t tmem_d = tmem_base + acc * L::kAccStride;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * L::kStageBytes;
+            const uint32_t sb = sa + L::kABytes;
+            const uint64_t adesc = A_MN ? umma_desc_sw128(sa, BK * 128, 1024) : umma_desc_sw128(sa, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_desc_sw128(sb, BK * 128, 1024) : umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = adesc + (A_MN ? (uint64_t)(k * 128) : (uint64_t)(k * 2));
-            const uint64_t bd = bdesc + (B_MN ? (uint64_t)(k * 128) : (uint64_t)(k * 2));
-            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = adesc + (A_MN ? (uint64_t)(k * 128) : (uint64_t)(k * 2));
+              const uint64_t bd = bdesc + (B_MN ? (uint64_t)(k * 128) : (uint64_t)(k * 2));
+              if (CTA2) umma_bf16_2cta(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CTA2) {
+              umma_commit_2cta(&empty_bar[stage]);                    // frees the slot in both CTAs
+              if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc]);   // accumulators complete -> both epilogues
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue
+    // ------------------------------------------------ epilogue (this CTA's 128 rows of the tile)
     const int ew = warp - 4;
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = ew >> 2;             // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = unit; w < total_work; w += nunits) {
       const int split = w / tiles;
       const int t = w - split * tiles;
       const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-      const int m0 = tm * BM, n0 = tn * BN;
+      const int m0 = tm * (BM * kNCta) + rank * BM;
+      const int n0 = tn * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int r = m0 + quad * 32 + lane;
       const bool row_ok = r < p.M;
-      const long long orow = r;
       const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
-      const bool add_bias = (p.bias != nullptr) && (split == 0);
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {
         const int n = n0 + half * kColsPerWarp + c;
         if (n >= p.N) break;  // warp-uniform
         uint32_t v[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + half * kColsPerWarp + c), v);
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + half * kColsPerWarp + c), v);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (add_bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-          }
-        }
-        if (row_ok) {
-          if (p.out2 != nullptr) {
-            uint4* o2 = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          } else if (p.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          if (p.aux_mode != 0) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (long long)r * p.ldaux + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 a = __ldg(a4 + j);
-              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 x = unpack_bf16(aw[q]);
-                if (p.aux_mode == 1) {
-                  f[8 * j + 2 * q] *= gelu_erf_grad(x.x);
-                  f[8 * j + 2 * q + 1] *= gelu_erf_grad(x.y);
-                } else {
-                  f[8 * j + 2 * q] = x.x > 0.0f ? f[8 * j + 2 * q] : 0.0f;
-                  f[8 * j + 2 * q + 1] = x.y > 0.0f ? f[8 * j + 2 * q + 1] : 0.0f;
-                }
-              }
-            }
-          }
-          if (p.residual != nullptr && split == 0) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 x = r4[j];
-              f[4 * j + 0] += x.x; f[4 * j + 1] += x.y; f[4 * j + 2] += x.z; f[4 * j + 3] += x.w;
-            }
-          }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
-            if (p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(f[4 * j]),
-                             "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                             : "memory");
-            } else {
-              float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            }
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o4[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-          }
-        }
+        epilogue_chunk(p, f, r, rrow, n, row_ok, split == 0);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      if (lane == 0) {
+        if (CTA2 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (CTA2) cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 2) {
+    if (CTA2) tmem_dealloc2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int CTA2>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
-  auto kfn = gemm_kernel<BN, A_MN, B_MN>;
+  auto kfn = gemm_kernel<BN, A_MN, B_MN, CTA2>;
+  using L = Cfg<BN, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::kTotal));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  kfn<<<grid, kThreads, SmemLayout<BN>::kTotal, st>>>(ta, tb, p);
-  VS_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, ta, tb, p));
   return 0;
+}
+
+template <int BN, int CTA2>
+static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                        cudaStream_t st) {
+  switch ((a_mn ? 2 : 0) | (b_mn ? 1 : 0)) {
+    case 0: return launch<BN, 0, 0, CTA2>(ta, tb, p, grid, st);
+    case 1: return launch<BN, 0, 1, CTA2>(ta, tb, p, grid, st);
+    case 2: return launch<BN, 1, 0, CTA2>(ta, tb, p, grid, st);
+    default: return launch<BN, 1, 1, CTA2>(ta, tb, p, grid, st);
+  }
+}
+
+struct TileChoice {
+  int cta2, bn, splits;
+};
+
+// Cost model: a 256xBN pair tile (cta_group::2) and a 128xBN single-CTA tile take about the same time per k-block
+// (the single CTA runs at half the tensor rate), so cost ~ waves * BN * k-blocks-per-work-item.
+static TileChoice choose_tiles(int M, int N, int kblocks, int nsm, bool allow_split, int forced_split, int forced_cfg) {
+  TileChoice best{0, 256, 1};
+  double best_cost = 1e30;
+  const int cand[5][2] = {{1, 256}, {1, 192}, {1, 128}, {0, 256}, {0, 128}};
+  for (int c = 0; c < 5; ++c) {
+    if (forced_cfg >= 0 && c != forced_cfg) continue;
+    const int cta2 = cand[c][0], bn = cand[c][1];
+    if (bn > 128 && N <= 128 && forced_cfg < 0) continue;
+    const int tm = (M + (cta2 ? 255 : 127)) / (cta2 ? 256 : 128);
+    const int tn = (N + bn - 1) / bn;
+    const int units = cta2 ? nsm / 2 : nsm;
+    const int max_s = forced_split > 0 ? forced_split : (allow_split ? 16 : 1);
+    for (int s = (forced_split > 0 ? forced_split : 1); s <= max_s; ++s) {
+      if (s > 1 && kblocks / s < 8 && forced_split <= 0) break;
+      const int work = tm * tn * s;
+      const int waves = (work + units - 1) / units;
+      const int kb = (kblocks + s - 1) / s;
+      // fixed per-work-item overhead (pipeline fill + epilogue drain) expressed in k-blocks
+      double cost = double(waves) * bn * (kb + 6.0);
+      if (!cta2) cost *= 1.02;  // prefer pairs on ties (less L2 traffic)
+      if (cost < best_cost) { best_cost = cost; best = {cta2, bn, s}; }
+    }
+  }
+  return best;
 }
 
 }  // namespace vs
@@ -317,35 +469,24 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   VS_CHECK_ARG(d->aux_mode == 0 || (d->aux != nullptr && d->ldaux % 8 == 0), "vs_gemm_bf16: aux missing/misaligned");
   VS_CHECK_ARG(d->out2 == nullptr || d->ldo2 % 8 == 0, "vs_gemm_bf16: ldo2 alignment");
   VS_CHECK_ARG(d->residual == nullptr || d->ldr % 4 == 0, "vs_gemm_bf16: ldr alignment");
+  VS_CHECK_ARG(d->split_k <= 1 || d->accumulate, "vs_gemm_bf16: split_k > 1 requires accumulate");
 
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_gemm_bf16: no CUDA device");
 
-  const int BN = (d->N <= 128) ? 128 : 256;
   GemmParams p{};
   p.M = d->M; p.N = d->N; p.K = d->K;
-  p.tiles_m = (d->M + BM - 1) / BM;
-  p.tiles_n = (d->N + BN - 1) / BN;
   p.kblocks = (d->K + BK - 1) / BK;
-  int splits = d->split_k;
-  const int tiles = p.tiles_m * p.tiles_n;
-  if (splits <= 0) {
-    splits = 1;
-    if (d->accumulate && tiles < nsm) {
-      // pick the split count with the best wave efficiency, keeping >= 8 k-blocks per split
-      double best = 0.0;
-      for (int s = 1; s <= 16; ++s) {
-        if (p.kblocks / s < 8 && s > 1) break;
-        const int work = tiles * s;
-        const double eff = double(work) / double(((work + nsm - 1) / nsm) * nsm);
-        if (eff > best + 1e-9) { best = eff; splits = s; }
-      }
-    }
-  }
-  VS_CHECK_ARG(splits == 1 || d->accumulate, "vs_gemm_bf16: split_k > 1 requires accumulate");
+  // tile_cfg: 0 automatic; 1..5 force {pair256, pair192, pair128, single256, single128} (tests / tuning)
+  const int forced_cfg = (d->tile_cfg >= 1 && d->tile_cfg <= 5) ? d->tile_cfg - 1 : -1;
+  TileChoice tc = choose_tiles(d->M, d->N, p.kblocks, nsm, d->accumulate != 0, d->split_k, forced_cfg);
+  int splits = tc.splits;
   if (splits > p.kblocks) splits = p.kblocks;
   // every split must own at least one k-block
   while (splits > 1 && (splits - 1) * ((p.kblocks + splits - 1) / splits) >= p.kblocks) --splits;
+  const int BN = tc.bn;
+  p.tiles_m = (d->M + (tc.cta2 ? 255 : 127)) / (tc.cta2 ? 256 : 128);
+  p.tiles_n = (d->N + BN - 1) / BN;
   p.splits = splits;
   p.out = d->out; p.ldo = d->ldo; p.out_f32 = d->out_dtype; p.accumulate = d->accumulate;
   p.bias = d->bias; p.act = d->act;
@@ -362,24 +503,23 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
     strides[0] = (uint64_t)d->lda * 2;
     int rc = make_tmap_bf16(&ta, d->A, 2, dims, strides, box);
     if (rc) return rc;
-    if (!d->b_mn_major) { dims[0] = d->K; dims[1] = d->N; box[0] = BK; box[1] = BN; }
+    const int bnh = tc.cta2 ? BN / 2 : BN;
+    if (!d->b_mn_major) { dims[0] = d->K; dims[1] = d->N; box[0] = BK; box[1] = bnh; }
     else                { dims[0] = d->N; dims[1] = d->K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)d->ldb * 2;
     rc = make_tmap_bf16(&tb, d->B, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const int total = tiles * splits;
-  const int grid = total < nsm ? total : nsm;
+  const int total = p.tiles_m * p.tiles_n * splits;
   cudaStream_t st = (cudaStream_t)stream;
-  const int key = (BN == 256 ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
-  switch (key) {
-    case 0: return launch<128, 0, 0>(ta, tb, p, grid, st);
-    case 1: return launch<128, 0, 1>(ta, tb, p, grid, st);
-    case 2: return launch<128, 1, 0>(ta, tb, p, grid, st);
-    case 3: return launch<128, 1, 1>(ta, tb, p, grid, st);
-    case 4: return launch<256, 0, 0>(ta, tb, p, grid, st);
-    case 5: return launch<256, 0, 1>(ta, tb, p, grid, st);
-    case 6: return launch<256, 1, 0>(ta, tb, p, grid, st);
-    default: return launch<256, 1, 1>(ta, tb, p, grid, st);
+  if (tc.cta2) {
+    const int pairs = nsm / 2;
+    const int grid = 2 * (total < pairs ? total : pairs);
+    if (BN == 256) return launch_major<256, 1>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
+    if (BN == 192) return launch_major<192, 1>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
+    return launch_major<128, 1>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
   }
+  const int grid = total < nsm ? total : nsm;
+  if (BN == 256) return launch_major<256, 0>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
+  return launch_major<128, 0>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
 }

@@ -58,7 +58,7 @@ def _rowmajor(t: torch.Tensor, what: str) -> int:
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=None, aux=None, aux_mode=AUX_NONE,
-         residual=None, row_tokens=0, accumulate=False, split_k=0, M=None, N=None, K=None):
+         residual=None, row_tokens=0, accumulate=False, split_k=0, tile_cfg=0, M=None, N=None, K=None):
     """out[M,N] = epilogue(sum_k A(m,k) B(n,k)); see include/vitseg.h:vs_gemm_desc.
 
     a: bf16 [M,K] (or [K,M] when a_mn); b: bf16 [N,K] (or [K,N] when b_mn); out: bf16 or fp32 2-D view."""
@@ -95,6 +95,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=Non
         d.residual, d.ldr = ptr(residual), _rowmajor(residual, "residual")
     d.row_tokens = row_tokens
     d.split_k = split_k
+    d.tile_cfg = tile_cfg
     if _GEMM_TIMING:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
