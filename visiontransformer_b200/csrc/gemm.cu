@@ -52,9 +52,12 @@ struct Cfg {
   static constexpr int kABytes = BM * BK * 2;                    // 16 KB
   static constexpr int kBAlloc = kBBoxes * 64 * BK * 2;          // smem reserved for B per stage
   static constexpr int kStageBytes = kABytes + kBAlloc;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kEpiBytes = kEpiWarps * 4096;             // one swizzled 32x32 fp32 staging tile per warp
+  static constexpr int kStages = (222 * 1024 - kEpiBytes) / kStageBytes > 8 ? 8 : (222 * 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int kEpiOffset = kStages * kStageBytes;
+  static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
   static constexpr int kAccStride = 256;                         // TMEM columns between accumulator stages
   static_assert(kStages >= 3, "pipeline too shallow");
 };
@@ -112,80 +115,46 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
 }
 
 // ------------------------------------------------------------------------------------------------
-// epilogue for one 32-row x 32-column chunk held as one row per thread
+// Epilogue math + I/O for 4 consecutive columns of one output row.  The epilogue warps transpose each 32x32
+// accumulator chunk through a swizzled smem tile so that here a warp covers 4 rows x 32 contiguous columns: every
+// global access (bias, residual, aux, out, out2) is a full-sector, row-contiguous request.  (The first version
+// stored one row per thread: 32 sectors per request; ncu r01 l1tex st sectors/request = 32, epilogue-bound.)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&f)[32], int r, long long rrow, int n,
-                                               bool row_ok, bool first_split) {
-  if (p.bias != nullptr && first_split) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-    }
-  }
-  if (!row_ok) return;
-  const long long orow = r;
-  if (p.out2 != nullptr) {
-    uint4* o2 = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-  }
+__device__ __forceinline__ void epilogue_quad(const GemmParams& p, float4 v, const float4& bias4, long long orow,
+                                              long long rrow, int n, bool first_split) {
+  if (first_split) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+  if (p.out2 != nullptr)
+    *reinterpret_cast<uint2*>(p.out2 + orow * p.ldo2 + n) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   if (p.act == 1) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   } else if (p.act == 2) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
   }
   if (p.aux_mode != 0) {
-    const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + orow * p.ldaux + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 a = __ldg(a4 + j);
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 x = unpack_bf16(aw[q]);
-        if (p.aux_mode == 1) {
-          f[8 * j + 2 * q] *= gelu_erf_grad(x.x);
-          f[8 * j + 2 * q + 1] *= gelu_erf_grad(x.y);
-        } else {
-          f[8 * j + 2 * q] = x.x > 0.0f ? f[8 * j + 2 * q] : 0.0f;
-          f[8 * j + 2 * q + 1] = x.y > 0.0f ? f[8 * j + 2 * q + 1] : 0.0f;
-        }
-      }
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.aux + orow * p.ldaux + n));
+    const float2 x0 = unpack_bf16(a.x), x1 = unpack_bf16(a.y);
+    if (p.aux_mode == 1) {
+      v.x *= gelu_erf_grad(x0.x); v.y *= gelu_erf_grad(x0.y); v.z *= gelu_erf_grad(x1.x); v.w *= gelu_erf_grad(x1.y);
+    } else {
+      v.x = x0.x > 0.0f ? v.x : 0.0f; v.y = x0.y > 0.0f ? v.y : 0.0f;
+      v.z = x1.x > 0.0f ? v.z : 0.0f; v.w = x1.y > 0.0f ? v.w : 0.0f;
     }
   }
   if (p.residual != nullptr && first_split) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 x = r4[j];
-      f[4 * j + 0] += x.x; f[4 * j + 1] += x.y; f[4 * j + 2] += x.z; f[4 * j + 3] += x.w;
-    }
+    const float4 x = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
+    v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
   }
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
     if (p.accumulate) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(f[4 * j]),
-                     "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                     : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
     } else {
-      float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      *reinterpret_cast<float4*>(o) = v;
     }
   } else {
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o4[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n) =
+        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
 }
 
@@ -348,20 +317,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int n0 = tn * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int r = m0 + quad * 32 + lane;
-      const bool row_ok = r < p.M;
-      const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
+      uint8_t* stg = smem + L::kEpiOffset + ew * 4096;
+      const int cq = lane & 7;           // this lane's column quad inside a 32-column chunk
+      const int rsub = lane >> 3;        // and its row inside each group of 4 rows
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {
-        const int n = n0 + half * kColsPerWarp + c;
-        if (n >= p.N) break;  // warp-uniform
+        const int nb = n0 + half * kColsPerWarp + c;
+        if (nb >= p.N) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + half * kColsPerWarp + c), v);
         tmem_ld_wait();
-        float f[32];
+        // transpose through smem: thread = row -> (4 rows x 8 column-quads) per warp request
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        epilogue_chunk(p, f, r, rrow, n, row_ok, split == 0);
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int n = nb + 4 * cq;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rsub;
+          const int r = m0 + quad * 32 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
+          if (r < p.M) {
+            const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
+            epilogue_quad(p, a, bias4, r, rrow, n, split == 0);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
