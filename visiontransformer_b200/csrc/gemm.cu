@@ -120,19 +120,14 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
 // global access (bias, residual, aux, out, out2) is a full-sector, row-contiguous request.  (The first version
 // stored one row per thread: 32 sectors per request; ncu r01 l1tex st sectors/request = 32, epilogue-bound.)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_quad(const GemmParams& p, float4 v, const float4& bias4, long long orow,
-                                              long long rrow, int n, bool first_split) {
-  if (first_split) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
-  if (p.out2 != nullptr)
-    *reinterpret_cast<uint2*>(p.out2 + orow * p.ldo2 + n) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+__device__ __forceinline__ float4 epilogue_math(const GemmParams& p, float4 v, uint2 aux) {
   if (p.act == 1) {
     v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   } else if (p.act == 2) {
     v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
   }
   if (p.aux_mode != 0) {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.aux + orow * p.ldaux + n));
-    const float2 x0 = unpack_bf16(a.x), x1 = unpack_bf16(a.y);
+    const float2 x0 = unpack_bf16(aux.x), x1 = unpack_bf16(aux.y);
     if (p.aux_mode == 1) {
       v.x *= gelu_erf_grad(x0.x); v.y *= gelu_erf_grad(x0.y); v.z *= gelu_erf_grad(x1.x); v.w *= gelu_erf_grad(x1.y);
     } else {
@@ -140,22 +135,7 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float4 v, con
       v.z = x1.x > 0.0f ? v.z : 0.0f; v.w = x1.y > 0.0f ? v.w : 0.0f;
     }
   }
-  if (p.residual != nullptr && first_split) {
-    const float4 x = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
-    v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-  }
-  if (p.out_f32) {
-    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
-    if (p.accumulate) {
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                   : "memory");
-    } else {
-      *reinterpret_cast<float4*>(o) = v;
-    }
-  } else {
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n) =
-        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-  }
+  return v;
 }
 
 template <int BN, int A_MN, int B_MN, int CTA2>
@@ -335,15 +315,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         __syncwarp();
         const int n = nb + 4 * cq;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        if (p.bias != nullptr && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        const int r0 = m0 + quad * 32 + rsub;                 // rows r0, r0+4, ..., r0+28
+        const bool use_res = p.residual != nullptr && split == 0;
+        // phase 1: issue every global load of the chunk (8 rows per lane) before any dependent math / store
+        uint2 auxv[8];
+        float4 resv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 4 * i;
+          auxv[i] = make_uint2(0u, 0u);
+          resv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < p.M) {
+            if (p.aux_mode != 0) auxv[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + (long long)r * p.ldaux + n));
+            if (use_res) {
+              const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
+              resv[i] = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
+            }
+          }
+        }
+        // phase 2: math and stores
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rsub;
-          const int r = m0 + quad * 32 + rl;
-          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
+          const int r = r0 + 4 * i;
+          float4 v = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
           if (r < p.M) {
-            const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
-            epilogue_quad(p, a, bias4, r, rrow, n, split == 0);
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (p.out2 != nullptr)
+              *reinterpret_cast<uint2*>(p.out2 + (long long)r * p.ldo2 + n) =
+                  make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            v = epilogue_math(p, v, auxv[i]);
+            v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w;
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + n;
+              if (p.accumulate) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z),
+                             "f"(v.w)
+                             : "memory");
+              } else {
+                *reinterpret_cast<float4*>(o) = v;
+              }
+            } else {
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n) =
+                  make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            }
           }
         }
         __syncwarp();
