@@ -120,22 +120,137 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
 // global access (bias, residual, aux, out, out2) is a full-sector, row-contiguous request.  (The first version
 // stored one row per thread: 32 sectors per request; ncu r01 l1tex st sectors/request = 32, epilogue-bound.)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 epilogue_math(const GemmParams& p, float4 v, uint2 aux) {
-  if (p.act == 1) {
-    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-  } else if (p.act == 2) {
-    v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
-  }
-  if (p.aux_mode != 0) {
-    const float2 x0 = unpack_bf16(aux.x), x1 = unpack_bf16(aux.y);
-    if (p.aux_mode == 1) {
-      v.x *= gelu_erf_grad(x0.x); v.y *= gelu_erf_grad(x0.y); v.z *= gelu_erf_grad(x1.x); v.w *= gelu_erf_grad(x1.y);
-    } else {
-      v.x = x0.x > 0.0f ? v.x : 0.0f; v.y = x0.y > 0.0f ? v.y : 0.0f;
-      v.z = x1.x > 0.0f ? v.z : 0.0f; v.w = x1.y > 0.0f ? v.w : 0.0f;
+__device__ __forceinline__ float act_fn(int act, float v) {
+  return act == 1 ? gelu_erf(v) : (act == 2 ? fmaxf(v, 0.0f) : v);
+}
+__device__ __forceinline__ float aux_fn(int mode, float v, float x) {
+  return mode == 1 ? v * gelu_erf_grad(x) : (x > 0.0f ? v : 0.0f);
+}
+
+// One warp's epilogue for one tile: kChunks chunks of 32 rows x 32 columns.
+//   * accumulators: tcgen05.ld (thread = row) -> swizzled smem transpose -> coalesced layout
+//       fp32 output : lane <-> 4 columns, 4 rows per request (8 iterations per chunk)
+//       bf16 output : lane <-> 8 columns, 8 rows per request (4 iterations per chunk)
+//   * software pipeline: bias for all chunks and the first chunk's residual / aux tile are requested BEFORE waiting for
+//     the accumulator; while chunk c is processed, the tcgen05.ld and the global loads of chunk c+1 are in flight.
+//     (ncu r01: the epilogue warps sat ~80 % of their time on long-scoreboard waits for tcgen05.ld and bias loads;
+//     with K = 768 the epilogue, not the MMA main loop, set the tile time.)
+template <int kChunks, bool OUT_F32>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint8_t* stg, uint32_t tmem_addr, uint64_t* tfull,
+                                              uint32_t tfull_phase, int row0, int col0, bool first_split, int lane) {
+  constexpr int CPL = OUT_F32 ? 4 : 8;        // columns per lane
+  constexpr int LPR = 32 / CPL;               // lanes per row
+  constexpr int RPI = 32 / LPR;               // rows per iteration (request)
+  constexpr int NIT = 32 / RPI;               // iterations per chunk
+  const int cl = lane % LPR;
+  const int rsub = lane / LPR;
+  const int r0 = row0 + rsub;
+  const bool use_bias = p.bias != nullptr && first_split;
+  const bool use_res = OUT_F32 && p.residual != nullptr && first_split;
+  const bool use_aux = !OUT_F32 && p.aux_mode != 0;
+
+  float4 bias_r[kChunks][CPL / 4];
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+    for (int h = 0; h < CPL / 4; ++h) {
+      bias_r[c][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int n = col0 + c * 32 + cl * CPL + 4 * h;
+      if (use_bias && n < p.N) bias_r[c][h] = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     }
+
+  float4 res_r[2][OUT_F32 ? NIT : 1];
+  uint4 aux_r[2][OUT_F32 ? 1 : NIT];
+  auto prefetch = [&](int c, int buf) {
+    const int n = col0 + c * 32 + cl * CPL;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int r = r0 + RPI * i;
+      const bool ok = r < p.M && n < p.N;
+      if (OUT_F32) {
+        res_r[buf][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (use_res && ok) {
+          const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
+          res_r[buf][i] = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
+        }
+      } else {
+        aux_r[buf][i] = make_uint4(0u, 0u, 0u, 0u);
+        if (use_aux && ok) aux_r[buf][i] = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)r * p.ldaux + n));
+      }
+    }
+  };
+  prefetch(0, 0);
+
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  uint32_t v[32];
+  tmem_ld32(tmem_addr, v);
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int nb = col0 + c * 32;
+    tmem_ld_wait();
+    // transpose through smem (16-byte slots XOR-swizzled by row: conflict-free both ways)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+          make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    if (c + 1 < kChunks) tmem_ld32(tmem_addr + (c + 1) * 32, v);   // in flight while this chunk is processed
+    __syncwarp();
+    if (c + 1 < kChunks) prefetch(c + 1, (c + 1) & 1);
+    if (nb < p.N) {
+      const int n = nb + cl * CPL;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int rl = rsub + RPI * i;
+        const int r = r0 + RPI * i;
+        float f[CPL];
+#pragma unroll
+        for (int h = 0; h < CPL / 4; ++h) {
+          const int slot = cl * (CPL / 4) + h;
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((slot ^ (rl & 7)) << 4));
+          f[4 * h + 0] = a.x + bias_r[c][h].x; f[4 * h + 1] = a.y + bias_r[c][h].y;
+          f[4 * h + 2] = a.z + bias_r[c][h].z; f[4 * h + 3] = a.w + bias_r[c][h].w;
+        }
+        if (r < p.M) {
+          if (OUT_F32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) f[k] = act_fn(p.act, f[k]);
+            const float4 rr = res_r[c & 1][i];
+            const float4 o4 = make_float4(f[0] + rr.x, f[1] + rr.y, f[2] + rr.z, f[3] + rr.w);
+            float* o = reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + n;
+            if (p.accumulate) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(o4.x), "f"(o4.y), "f"(o4.z),
+                           "f"(o4.w)
+                           : "memory");
+            } else {
+              *reinterpret_cast<float4*>(o) = o4;
+            }
+          } else {
+            if (p.out2 != nullptr)
+              *reinterpret_cast<uint4*>(p.out2 + (long long)r * p.ldo2 + n) =
+                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            if (p.act != 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = act_fn(p.act, f[k]);
+            }
+            if (use_aux) {
+              const uint4 a = aux_r[c & 1][i];
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 x = unpack_bf16(aw[k]);
+                f[2 * k] = aux_fn(p.aux_mode, f[2 * k], x.x);
+                f[2 * k + 1] = aux_fn(p.aux_mode, f[2 * k + 1], x.y);
+              }
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n) =
+                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
-  return v;
 }
 
 template <int BN, int A_MN, int B_MN, int CTA2>
@@ -287,83 +402,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = ew >> 2;             // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
+    constexpr int kChunks = kColsPerWarp / 32;
+    uint8_t* stg = smem + L::kEpiOffset + ew * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = unit; w < total_work; w += nunits) {
       const int split = w / tiles;
       const int t = w - split * tiles;
       const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-      const int m0 = tm * (BM * kNCta) + rank * BM;
-      const int n0 = tn * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      uint8_t* stg = smem + L::kEpiOffset + ew * 4096;
-      const int cq = lane & 7;           // this lane's column quad inside a 32-column chunk
-      const int rsub = lane >> 3;        // and its row inside each group of 4 rows
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        const int nb = n0 + half * kColsPerWarp + c;
-        if (nb >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + half * kColsPerWarp + c), v);
-        tmem_ld_wait();
-        // transpose through smem: thread = row -> (4 rows x 8 column-quads) per warp request
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-              make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
-        const int n = nb + 4 * cq;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        const int r0 = m0 + quad * 32 + rsub;                 // rows r0, r0+4, ..., r0+28
-        const bool use_res = p.residual != nullptr && split == 0;
-        // phase 1: issue every global load of the chunk (8 rows per lane) before any dependent math / store
-        uint2 auxv[8];
-        float4 resv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 4 * i;
-          auxv[i] = make_uint2(0u, 0u);
-          resv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < p.M) {
-            if (p.aux_mode != 0) auxv[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + (long long)r * p.ldaux + n));
-            if (use_res) {
-              const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
-              resv[i] = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
-            }
-          }
-        }
-        // phase 2: math and stores
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + rsub;
-          const int r = r0 + 4 * i;
-          float4 v = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
-          if (r < p.M) {
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if (p.out2 != nullptr)
-              *reinterpret_cast<uint2*>(p.out2 + (long long)r * p.ldo2 + n) =
-                  make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-            v = epilogue_math(p, v, auxv[i]);
-            v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w;
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + n;
-              if (p.accumulate) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z),
-                             "f"(v.w)
-                             : "memory");
-              } else {
-                *reinterpret_cast<float4*>(o) = v;
-              }
-            } else {
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n) =
-                  make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-            }
-          }
-        }
-        __syncwarp();
-      }
+      const int row0 = tm * (BM * kNCta) + rank * BM + quad * 32;
+      const int col0 = tn * BN + half * kColsPerWarp;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + half * kColsPerWarp);
+      if (p.out_f32)
+        epilogue_tile<kChunks, true>(p, stg, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
+      else
+        epilogue_tile<kChunks, false>(p, stg, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
