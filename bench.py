@@ -175,7 +175,8 @@ def run_ours(args):
     C = MODEL["num_classes"]
 
     torch.manual_seed(0)
-    lm = LightningViTModel(**MODEL, image_size=IMAGE, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    # reference defaults (model/CE/classes.py:233-234): hidden and attention dropout 0.1, active in train()
+    lm = LightningViTModel(**MODEL, image_size=IMAGE, hidden_dropout_prob=args.dropout, attention_probs_dropout_prob=args.dropout)
     lm = lm.to(dev).train()
     # model/CE/classes.py:296-297; capturable so that the whole step can live in one CUDA graph
     opt = torch.optim.Adam(lm.parameters(), lr=1e-5, fused=True, capturable=True)
@@ -321,7 +322,7 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "ViT-B/16 CE segmentation training, batch 64/GPU, 224x224, C=17 (BASELINE configs[1])",
                        "global_batch": B * world, "parallelism": f"dp{world}", "optimizer": "Adam(lr=1e-5, fused, capturable) in timed region", "cuda_graph": graphed is not None,
-                       "dropout": 0.0, "l2": "working set (4.2 GB activations + 0.9 GB weights/grads per step) >> 126 MB L2; no flush needed",
+                       "dropout": args.dropout, "l2": "working set (4.2 GB activations + 0.9 GB weights/grads per step) >> 126 MB L2; no flush needed",
                        "label_resize": "256->224 nearest inside the step, as LightningViTModel.training_step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "note": "pinned host batch prefetched one step ahead on a copy stream"},
@@ -348,6 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="hidden/attention dropout (reference default 0.1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -80,6 +80,11 @@ typedef struct vs_gemm_desc {
   int32_t row_tokens;
   int32_t split_k;
   int32_t tile_cfg; /* 0 = automatic; 1..5 force {pair 256xBN256, pair BN192, pair BN128, single-CTA BN256, BN128} */
+  /* hidden-state dropout (ViTSelfOutput / ViTOutput, TF:267,310): v = keep ? v/(1-p) : 0 applied after bias/act and
+   * before the residual add; fp32 outputs only.  dropout_seed is a DEVICE pointer to the per-step counter. */
+  float dropout_p;
+  const uint32_t* dropout_seed;
+  uint32_t dropout_site;
 } vs_gemm_desc;
 
 int vs_gemm_bf16(const vs_gemm_desc* d, void* stream);
@@ -92,13 +97,16 @@ int vs_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* out,
  * LayerNorm (TF:325-326,333,340,416,455; eps 1e-12), fp32 residual stream in, bf16 (and/or fp32) out.
  *   x fp32 [M, D]; gamma/beta fp32 [D]; y_bf16 and/or y_f32 may be NULL; mean/rstd fp32 [M] may be NULL (inference).
  * Backward: dx_out[M,D] (fp32) = dx_in (nullable: skip-connection gradient) + LN'(dy); dgamma/dbeta accumulate (+=).
- *   dy is bf16 or fp32 (dy_is_f32); dx_bf16 (nullable) receives a bf16 copy of dx_out.
+ *   dy is bf16 or fp32 (dy_is_f32); dx_bf16 (nullable) receives a bf16 copy of dx_out, multiplied by the dropout
+ *   mask of site `dropout_site` when dropout_p > 0 (it feeds the backward GEMMs of the projection whose output was
+ *   dropped out in forward).
  * ------------------------------------------------------------------------------------------------ */
 int vs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t M, int32_t D,
                      void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
 int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const float* gamma, const float* mean,
                      const float* rstd, const float* dx_in, int32_t M, int32_t D, float* dx_out, void* dx_bf16,
-                     float* dgamma, float* dbeta, void* stream);
+                     float* dgamma, float* dbeta, float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-head self-attention (TF:220-251 + sdpa_attention_forward): softmax(Q K^T * scale) V per (batch, head).
@@ -107,11 +115,14 @@ int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const fl
  *   lse  fp32 [B, H, N]  natural-log row logsumexp of the scaled scores (saved for backward; may be NULL)
  * Backward: dctx bf16 [B,N,H,64] -> dqkv bf16 [B,N,3,H,64].  dq_accum is an fp32 [B,N,H,64] scratch,
  *   delta an fp32 [B,H,N] scratch; both caller-provided.
+ * dropout_p > 0 drops attention probabilities (attention_probs_dropout_prob, SDPA dropout_p) with a counter-based
+ *   mask regenerated identically in backward.
  * ------------------------------------------------------------------------------------------------ */
 int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t B, int32_t N, int32_t H, float scale,
-                     void* stream);
+                     float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site, void* stream);
 int vs_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                     float* dq_accum, float* delta, int32_t B, int32_t N, int32_t H, float scale, void* stream);
+                     float* dq_accum, float* delta, int32_t B, int32_t N, int32_t H, float scale, float dropout_p,
+                     const uint32_t* dropout_seed, uint32_t dropout_site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding glue (TF:100-128, 153-167)
@@ -194,6 +205,16 @@ int vs_paed_multiclass(const float* low, const int64_t* labels, float* t1, float
  * penalty = 2 msk (1 - prob) when class_penalty else 1; dprob (nullable) = d(sum)/d prob (overwritten). */
 int vs_paed_multiclass_dense(const float* msk, const float* prob, float* t1, float* t2, float* t3, float* loss_sum,
                              float* dprob, int32_t B, int32_t C, int32_t S, int32_t class_penalty, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dropout glue.  vs_dropout_rows: in-place dropout of an fp32 buffer of n elements (n % 4 == 0) + optional bf16 copy —
+ * the embedding dropout (TF:126) in forward and the same mask on the gradient in backward.  vs_dropout_mask writes
+ * the keep mask of a site as bytes (scheme 0: hidden-state pair hash, scheme 1: attention per-element hash); tests.
+ * ------------------------------------------------------------------------------------------------ */
+int vs_dropout_rows(float* x, void* x_bf16, int64_t n, float dropout_p, const uint32_t* dropout_seed,
+                    uint32_t dropout_site, void* stream);
+int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, float dropout_p, const uint32_t* dropout_seed,
+                    uint32_t dropout_site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight shadows: fp32 master -> bf16 copy (one pass), plus utility conversions.

@@ -1,0 +1,196 @@
+"""GPU (-m gpu): dropout (hidden_dropout_prob / attention_probs_dropout_prob, model/CE/classes.py:233-234).
+
+torch's RNG stream cannot be bit-matched, so the kernels are checked EXACTLY against PyTorch fp32
+math that uses the kernels' own masks (exported by vs_dropout_mask), plus keep-rate statistics and module-level
+train/eval behaviour."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def _mask(K, n, scheme, drop):
+    return K.dropout_mask(torch.empty(n, device=drop[1].device, dtype=torch.uint8), scheme, drop).float()
+
+
+def test_mask_statistics_and_determinism():
+    from visiontransformer_b200 import kernels as K
+    dev = _dev()
+    seed = torch.tensor([1234], device=dev, dtype=torch.int32)
+    n = 1 << 22
+    for p in (0.1, 0.5):
+        for scheme in (0, 1):
+            m = _mask(K, n, scheme, (p, seed, 7))
+            assert abs(m.mean().item() - (1 - p)) < 2e-3
+            assert torch.equal(m, _mask(K, n, scheme, (p, seed, 7)))
+            m2 = _mask(K, n, scheme, (p, seed, 8))          # other site -> independent mask
+            assert abs((m * m2).mean().item() - (1 - p) ** 2) < 3e-3
+    seed2 = seed + 1                                          # next step -> independent mask
+    a, b = _mask(K, n, 0, (0.1, seed, 3)), _mask(K, n, 0, (0.1, seed2, 3))
+    assert abs((a * b).mean().item() - 0.81) < 3e-3
+
+
+def test_gemm_epilogue_dropout_and_layernorm_bwd_mask():
+    from visiontransformer_b200 import kernels as K
+    dev = _dev()
+    torch.manual_seed(0)
+    M, N, Kd, p = 1000, 768, 512, 0.1
+    seed = torch.tensor([99], device=dev, dtype=torch.int32)
+    drop = (p, seed, 5)
+    a = torch.randn(M, Kd, device=dev).bfloat16()
+    w = (torch.randn(N, Kd, device=dev) * 0.1).bfloat16()
+    bias, res = torch.randn(N, device=dev), torch.randn(M, N, device=dev)
+    out = torch.empty(M, N, device=dev)
+    K.gemm(a, w, out, bias=bias, residual=res, dropout=drop)
+    mask = _mask(K, M * N, 0, drop).view(M, N)
+    thresh = round(p * 65536)
+    scale = 1.0 / (1.0 - thresh / 65536.0)
+    ref = (a.float() @ w.float().t() + bias) * mask * scale + res
+    assert _rel(out, ref) < 1e-5
+    # LayerNorm backward: fp32 dx unmasked, bf16 copy masked with the same site
+    D = N
+    x = torch.randn(M, D, device=dev)
+    g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+    mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    y = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    K.layernorm_fwd(x, g, b, 1e-12, y, None, mean, rstd)
+    dy = torch.randn(M, D, device=dev)
+    dx, dx16 = torch.empty(M, D, device=dev), torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    K.layernorm_bwd(dy, x, g, mean, rstd, None, dx, dx16, dg, db, dropout=drop)
+    xr = x.clone().requires_grad_(True)
+    F.layer_norm(xr, (D,), g, b, 1e-12).backward(dy)
+    assert _rel(dx, xr.grad) < 1e-4
+    assert _rel(dx16, xr.grad * mask * scale) < 1e-2
+    assert ((dx16 == 0) == (mask == 0)).float().mean().item() > 0.999
+    # dropout_rows: in place + bf16 copy
+    z = torch.randn(M, D, device=dev)
+    z0 = z.clone()
+    z16 = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    K.dropout_rows(z, z16, drop)
+    assert _rel(z, z0 * mask * scale) < 1e-6
+    assert _rel(z16, z) < 1e-2
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (1, 300, 2)])
+def test_attention_dropout_forward_backward(B, N, H):
+    from visiontransformer_b200 import kernels as K
+    dev = _dev()
+    torch.manual_seed(1)
+    p = 0.1
+    seed = torch.tensor([4242], device=dev, dtype=torch.int32)
+    drop = (p, seed, 1003)
+    D = H * 64
+    qkv = torch.randn(B, N, 3, H, 64, device=dev).bfloat16()
+    ctx = torch.empty(B, N, H, 64, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=dev)
+    K.attention_fwd(qkv, ctx, lse, B, N, H, 0.125, dropout=drop)
+    mask = _mask(K, B * H * N * N, 1, drop).view(B, H, N, N)
+    scale = 1.0 / (1.0 - round(p * 65536) / 65536.0)
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).float().requires_grad_(True) for i in range(3)]
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    ref = (torch.softmax(s, -1) * mask * scale) @ v
+    assert _rel(ctx.permute(0, 2, 1, 3), ref) < 1e-2
+    assert _rel(lse, torch.logsumexp(s, -1)) < 1e-3
+    dctx = torch.randn(B, N, H, 64, device=dev).bfloat16()
+    ref.backward(dctx.permute(0, 2, 1, 3).float())
+    dqkv = torch.zeros(B, N, 3, H, 64, device=dev, dtype=torch.bfloat16)
+    dq_acc, delta = torch.empty(B, N, D, device=dev), torch.empty(B, H, N, device=dev)
+    K.attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_acc, delta, B, N, H, 0.125, dropout=drop)
+    assert _rel(dqkv[:, :, 1].permute(0, 2, 1, 3), k.grad) < 2e-2
+    assert _rel(dqkv[:, :, 2].permute(0, 2, 1, 3), v.grad) < 2e-2
+    assert _rel(dq_acc.view(B, N, H, 64).permute(0, 2, 1, 3), q.grad) < 2e-2
+
+
+def test_module_train_eval_dropout_semantics():
+    """train(): dropout on (different masks per step, loss finite, gradients flow); eval(): deterministic and equal to
+    the dropout-free model; same seed -> same result."""
+    from oracle import vitseg_oracle as O
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    dev = _dev()
+    cfg = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=128, num_hidden_layers=2, num_attention_heads=2)
+    sd = O.seeded_state_dict(cfg, 7, head_gain=4.0)
+    m = LightningViTModel(17, 16, 128, 2, 2)     # reference defaults: p = 0.1 / 0.1
+    m.load_state_dict(O.to_module_state_dict(sd, "model."), strict=True)
+    m = m.to(dev)
+    x = O.synthetic_images(2, 224, seed=11).to(dev)
+    y = O.synthetic_labels(2, 17, seed=12).to(dev)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(x), m(x)
+        ref = O.forward(sd, x.cpu(), cfg)
+    assert torch.equal(e1, e2)
+    assert _rel(e1.cpu(), ref) < 1e-2
+    m.train()
+    eng = m.model.engine
+    eng.seed_dropout(5)
+    l1 = m.training_step((x, y), 0)
+    l1.backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    l2 = m.training_step((x, y), 1)              # counter advanced -> different masks
+    eng.seed_dropout(5)
+    l3 = m.training_step((x, y), 2)              # same counter -> identical result
+    l3.backward()
+    assert torch.isfinite(l1) and l1.item() != l2.item()
+    assert l1.item() == l3.item()
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert _rel(p.grad, g1[k]) < 1e-3, k   # atomics reorder sums: not bitwise
+    with torch.no_grad():
+        m.eval()
+        lo = m._loss(x, y).item()
+    assert abs(l1.item() - lo) / lo < 0.2          # dropout perturbs, it does not destroy
+
+
+def test_dropout_gradient_matches_finite_difference():
+    """with a fixed dropout counter the training-mode network is a deterministic function: its analytic gradient must
+    match central finite differences of the fused loss along a random direction (checks every mask is regenerated
+    consistently in backward)."""
+    from oracle import vitseg_oracle as O
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    dev = _dev()
+    cfg = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=128, num_hidden_layers=2, num_attention_heads=2)
+    sd = O.seeded_state_dict(cfg, 9, head_gain=4.0)
+    m = LightningViTModel(17, 16, 128, 2, 2, hidden_dropout_prob=0.2, attention_probs_dropout_prob=0.2)
+    m.load_state_dict(O.to_module_state_dict(sd, "model."), strict=True)
+    m = m.to(dev).train()
+    x = O.synthetic_images(2, 224, seed=3).to(dev)
+    y = O.synthetic_labels(2, 17, seed=4).to(dev)
+    eng = m.model.engine
+
+    def loss_at():
+        eng.seed_dropout(77)
+        return m.training_step((x, y), 0)
+
+    loss_at().backward()
+    names = ["model.seg_head.0.bias", "model.backbone.encoder.layer.1.output.dense.bias",
+             "model.backbone.encoder.layer.0.attention.attention.value.bias", "model.backbone.embeddings.cls_token"]
+    params = dict(m.named_parameters())
+    for name in names:
+        p = params[name]
+        g = p.grad.clone()
+        d = torch.randn_like(p)
+        d = d / d.norm()
+        eps = 2e-2
+        with torch.no_grad():
+            p.add_(eps * d)
+            lp = loss_at().item()
+            p.sub_(2 * eps * d)
+            lm = loss_at().item()
+            p.add_(eps * d)
+        fd = (lp - lm) / (2 * eps)
+        an = (g * d).sum().item()
+        assert abs(fd - an) <= 0.15 * max(abs(an), abs(fd)) + 2e-4, (name, fd, an)

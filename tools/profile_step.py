@@ -10,13 +10,15 @@ from visiontransformer_b200.ce.classes import LightningViTModel  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--dropout", type=float, default=0.1)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--mode", default="train", choices=["train", "infer"])
 args = ap.parse_args()
+DROP = args.dropout
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-m = LightningViTModel(17, 16, 768, 12, 12, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0).to(dev).train()
+m = LightningViTModel(17, 16, 768, 12, 12, hidden_dropout_prob=DROP, attention_probs_dropout_prob=DROP).to(dev).train()
 opt = torch.optim.Adam(m.parameters(), lr=1e-5, fused=True)
 x = torch.rand(args.batch, 3, 224, 224, device=dev)
 y = torch.randint(0, 17, (args.batch, 256, 256), device=dev)

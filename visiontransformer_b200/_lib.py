@@ -28,6 +28,7 @@ class GemmDesc(C.Structure):
         ("aux", c_void_p), ("ldaux", c_i64), ("aux_mode", c_int),
         ("residual", c_void_p), ("ldr", c_i64),
         ("row_tokens", c_int), ("split_k", c_int), ("tile_cfg", c_int),
+        ("dropout_p", c_float), ("dropout_seed", c_void_p), ("dropout_site", C.c_uint32),
     ]
 
 
@@ -40,10 +41,13 @@ _SIGS = {
     "vs_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p],
     "vs_layernorm_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                         c_void_p, c_void_p, c_void_p, c_void_p],
-    "vs_attention_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
+                         c_void_p, c_void_p, c_void_p, c_float, c_void_p, C.c_uint32, c_void_p],
+    "vs_attention_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, C.c_uint32,
+                         c_void_p],
     "vs_attention_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                         c_float, c_void_p],
+                         c_float, c_float, c_void_p, C.c_uint32, c_void_p],
+    "vs_dropout_rows": [c_void_p, c_void_p, c_i64, c_float, c_void_p, C.c_uint32, c_void_p],
+    "vs_dropout_mask": [c_void_p, c_i64, c_int, c_float, c_void_p, C.c_uint32, c_void_p],
     "vs_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_cls_rows": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -53,7 +53,7 @@ struct AttnFwdSmem {
 
 __global__ void __launch_bounds__(160, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
-                float* __restrict__ lse, int B, int N, int H, float scale) {
+                float* __restrict__ lse, int B, int N, int H, float scale, const DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::kBar);
@@ -145,6 +145,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     const uint32_t lane_off = uint32_t(warp * 32) << 16;
     uint8_t* sP = smem + AttnFwdSmem::kP;
     const float sl2 = scale * kLog2e;
+    const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)N;
     float m_run = -INFINITY, l_run = 0.0f;
     float o_acc[kDH];
 #pragma unroll
@@ -179,8 +181,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float pv = (c + i < nvalid) ? exp2f(__uint_as_float(v[i]) * sl2 - m_new) : 0.0f;
+          l_blk += pv;   // the softmax normaliser uses the un-dropped probabilities (dropout acts on softmax output)
           f[i] = pv;
-          l_blk += pv;
+          if (drop.thresh != 0u)
+            f[i] = drop_keep(drow + (uint32_t)(kv0 + c + i), dseed, drop.thresh) ? pv * drop.scale : 0.0f;
         }
         store_row32_sw128(sP, r, c >> 5, f);
       }
@@ -256,7 +260,7 @@ struct AttnBwdSmem {
 __global__ void __launch_bounds__(160, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                float* __restrict__ dq_accum, int B, int N, int H, float scale) {
+                float* __restrict__ dq_accum, int B, int N, int H, float scale, const DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBar);
@@ -367,9 +371,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint8_t* sP = smem + AttnBwdSmem::kP;
     uint8_t* sDS = smem + AttnBwdSmem::kDS;
     const float sl2 = scale * kLog2e;
+    const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
     for (int i = 0; i < nq; ++i) {
       const uint32_t ph = i & 1;
       const int q = i * kBQ + r;
+      const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)N;
       const bool q_ok = q < N;
       float lse2 = 0.0f, dlt = 0.0f;
       if (q_ok) {
@@ -389,8 +395,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           for (int k = 0; k < 32; ++k) {
             const bool ok = q_ok && (c + k < nvalid_kv);
             const float pv = ok ? exp2f(__uint_as_float(sv[k]) * sl2 - lse2) : 0.0f;
-            pf[k] = pv;
-            dsf[k] = pv * (__uint_as_float(dv[k]) - dlt) * scale;
+            float pd = pv, dpv = __uint_as_float(dv[k]);
+            if (drop.thresh != 0u) {
+              // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
+              const bool keep = drop_keep(drow + (uint32_t)(kv0 + c + k), dseed, drop.thresh);
+              pd = keep ? pv * drop.scale : 0.0f;
+              dpv = keep ? dpv * drop.scale : 0.0f;
+            }
+            pf[k] = pd;
+            dsf[k] = pv * (dpv - dlt) * scale;
           }
         } else {
 #pragma unroll
@@ -460,8 +473,23 @@ static int make_tok_tmap(CUtensorMap* m, const void* base, int B, int N, int row
 
 using namespace vs;
 
+static int make_drop(DropCfg* dc, float p, const uint32_t* seed, uint32_t site, long long index_space) {
+  dc->thresh = 0u; dc->scale = 1.0f; dc->seed = nullptr; dc->site = 0u;
+  if (p > 0.0f) {
+    if (!(p < 1.0f) || seed == nullptr || index_space >= (1LL << 32)) {
+      set_error("attention dropout: need 0<p<1, a device seed pointer and B*H*N*N < 2^32");
+      return -1;
+    }
+    dc->thresh = (uint32_t)(p * 65536.0f + 0.5f);
+    dc->scale = 1.0f / (1.0f - (float)dc->thresh / 65536.0f);
+    dc->seed = seed;
+    dc->site = site;
+  }
+  return 0;
+}
+
 extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t B, int32_t N, int32_t H, float scale,
-                                void* stream) {
+                                float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site, void* stream) {
   VS_CHECK_ARG(qkv && ctx, "vs_attention_fwd: null pointer");
   VS_CHECK_ARG(B > 0 && N > 0 && H > 0, "vs_attention_fwd: bad shape");
   VS_CHECK_ARG(B <= 65535 && H <= 65535, "vs_attention_fwd: B/H exceed grid limits");
@@ -475,16 +503,18 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
                                        AttnFwdSmem::kTotal));
     attr = true;
   }
+  DropCfg dc;
+  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * N)) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
   attn_fwd_kernel<<<grid, 160, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, (__nv_bfloat16*)ctx, lse, B, N, H,
-                                                                           scale);
+                                                                           scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                                 float* dq_accum, float* delta, int32_t B, int32_t N, int32_t H, float scale,
-                                void* stream) {
+                                float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site, void* stream) {
   VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && dq_accum && delta, "vs_attention_bwd: null pointer");
   VS_CHECK_ARG(B > 0 && N > 0 && H > 0, "vs_attention_bwd: bad shape");
   VS_CHECK_ARG(B <= 65535 && H <= 65535, "vs_attention_bwd: B/H exceed grid limits");
@@ -507,9 +537,11 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
                                                                 delta, B, N, H);
   VS_CHECK_LAUNCH();
   VS_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * N * D * sizeof(float), st));
+  DropCfg dc;
+  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * N)) return rc2;
   dim3 grid((N + kBKV - 1) / kBKV, H, B);
   attn_bwd_kernel<<<grid, 160, AttnBwdSmem::kTotal, st>>>(tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, dq_accum, B, N, H,
-                                                          scale);
+                                                          scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }

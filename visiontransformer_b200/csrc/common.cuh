@@ -107,6 +107,38 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Counter-based dropout masks (hidden_dropout_prob / attention_probs_dropout_prob = 0.1, model/CE/classes.py:233-234).
+// mask(site, element) = hash(element index, seed(step, site)): nothing is stored; backward regenerates the mask.
+// A 32-bit murmur-style finaliser yields two 16-bit uniforms; keep iff u16 >= round(p * 65536).
+// ----------------------------------------------------------------------------------------------
+struct DropCfg {
+  uint32_t thresh;        // 0 = dropout off
+  float scale;            // 1 / (1 - p)
+  const uint32_t* seed;   // device pointer: per-step counter (CUDA-graph replays advance it on the device)
+  uint32_t site;
+};
+__device__ __forceinline__ uint32_t drop_seed(const DropCfg& d) {
+  return d.seed[0] * 0x9E3779B9u + d.site * 0x85EBCA6Bu + 0x27D4EB2Fu;
+}
+__device__ __forceinline__ uint32_t drop_hash(uint32_t x, uint32_t seed) {
+  x ^= seed;
+  x *= 0x9E3779B1u; x ^= x >> 16;
+  x *= 0x85EBCA6Bu; x ^= x >> 13;
+  x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+// per-element form (attention probabilities)
+__device__ __forceinline__ bool drop_keep(uint32_t elem, uint32_t seed, uint32_t thresh) {
+  return (drop_hash(elem, seed) & 0xFFFFu) >= thresh;
+}
+// pair form (hidden states): elements 2k and 2k+1 share one hash; `elem` must be even
+__device__ __forceinline__ void drop_keep2(uint32_t elem, uint32_t seed, uint32_t thresh, bool& k0, bool& k1) {
+  const uint32_t h = drop_hash(elem >> 1, seed);
+  k0 = (h & 0xFFFFu) >= thresh;
+  k1 = (h >> 16) >= thresh;
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -43,6 +43,7 @@ struct GemmParams {
   const float* residual;
   long long ldr;
   int row_tokens;
+  DropCfg drop;  // hidden-state dropout applied to (acc + bias) before the residual add (fp32 outputs only)
 };
 
 template <int BN, int CTA2>
@@ -215,6 +216,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint8_t* stg,
           if (OUT_F32) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) f[k] = act_fn(p.act, f[k]);
+            if (p.drop.thresh != 0u) {   // TF:267 / TF:310: dropout(dense(x)) then + residual
+              const uint32_t sd = drop_seed(p.drop);
+              const uint32_t e = (uint32_t)r * (uint32_t)p.N + (uint32_t)n;
+              bool k0, k1, k2, k3;
+              drop_keep2(e, sd, p.drop.thresh, k0, k1);
+              drop_keep2(e + 2, sd, p.drop.thresh, k2, k3);
+              f[0] = k0 ? f[0] * p.drop.scale : 0.0f; f[1] = k1 ? f[1] * p.drop.scale : 0.0f;
+              f[2] = k2 ? f[2] * p.drop.scale : 0.0f; f[3] = k3 ? f[3] * p.drop.scale : 0.0f;
+            }
             const float4 rr = res_r[c & 1][i];
             const float4 o4 = make_float4(f[0] + rr.x, f[1] + rr.y, f[2] + rr.z, f[3] + rr.w);
             float* o = reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + n;
@@ -615,6 +625,16 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   p.out2 = (__nv_bfloat16*)d->out2; p.ldo2 = d->ldo2;
   p.aux = (const __nv_bfloat16*)d->aux; p.ldaux = d->ldaux; p.aux_mode = d->aux_mode;
   p.residual = d->residual; p.ldr = d->ldr; p.row_tokens = d->row_tokens;
+  p.drop.thresh = 0; p.drop.scale = 1.0f; p.drop.seed = nullptr; p.drop.site = 0;
+  if (d->dropout_p > 0.0f) {
+    VS_CHECK_ARG(d->dropout_p < 1.0f && d->dropout_seed != nullptr && d->out_dtype == 1 && !d->accumulate,
+                 "vs_gemm_bf16: dropout needs 0<p<1, a device seed pointer and a non-accumulating fp32 output");
+    VS_CHECK_ARG((long long)d->M * d->N < (1LL << 32), "vs_gemm_bf16: dropout index space exceeds 2^32");
+    p.drop.thresh = (uint32_t)(d->dropout_p * 65536.0f + 0.5f);
+    p.drop.scale = 1.0f / (1.0f - (float)p.drop.thresh / 65536.0f);
+    p.drop.seed = d->dropout_seed;
+    p.drop.site = d->dropout_site;
+  }
 
   CUtensorMap ta, tb;
   {

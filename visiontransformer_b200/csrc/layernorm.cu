@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dx_in, int M,
               float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-              float* __restrict__ dbeta) {
+              float* __restrict__ dbeta, const DropCfg drop) {
   constexpr int D = NV * 128;
   __shared__ float s_dg[D];
   __shared__ float s_db[D];
@@ -113,9 +113,20 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       reinterpret_cast<float4*>(dx_out + (size_t)row * D)[lane + 32 * i] = o;
-      if (dx_bf16)
+      if (dx_bf16) {
+        if (drop.thresh != 0u) {
+          // the bf16 copy feeds the dgrad/wgrad of the GEMM whose output was dropped out in forward: d(acc) = m*dy/(1-p)
+          const uint32_t e = (uint32_t)row * (uint32_t)D + (uint32_t)(lane + 32 * i) * 4u;
+          const uint32_t sd = drop_seed(drop);
+          bool k0, k1, k2, k3;
+          drop_keep2(e, sd, drop.thresh, k0, k1);
+          drop_keep2(e + 2, sd, drop.thresh, k2, k3);
+          o.x = k0 ? o.x * drop.scale : 0.0f; o.y = k1 ? o.y * drop.scale : 0.0f;
+          o.z = k2 ? o.z * drop.scale : 0.0f; o.w = k3 ? o.w * drop.scale : 0.0f;
+        }
         reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[lane + 32 * i] =
             make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
     }
   }
 #pragma unroll
@@ -156,7 +167,8 @@ extern "C" int vs_layernorm_fwd(const float* x, const float* gamma, const float*
 
 extern "C" int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const float* gamma,
                                 const float* mean, const float* rstd, const float* dx_in, int32_t M, int32_t D,
-                                float* dx_out, void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+                                float* dx_out, void* dx_bf16, float* dgamma, float* dbeta, float dropout_p,
+                                const uint32_t* dropout_seed, uint32_t dropout_site, void* stream) {
   VS_CHECK_ARG(dy && x && gamma && mean && rstd && dx_out && dgamma && dbeta, "vs_layernorm_bwd: null pointer");
   VS_CHECK_ARG(M > 0 && D > 0 && D % 128 == 0 && D <= 1024, "vs_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
   const int nsm = sm_count();
@@ -165,11 +177,19 @@ extern "C" int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* 
   int grid = nsm * 4;
   if (grid > (M + 7) / 8) grid = (M + 7) / 8;
   __nv_bfloat16* db = (__nv_bfloat16*)dx_bf16;
+  DropCfg dc{0u, 1.0f, nullptr, 0u};
+  if (dropout_p > 0.0f) {
+    VS_CHECK_ARG(dropout_p < 1.0f && dropout_seed != nullptr, "vs_layernorm_bwd: bad dropout arguments");
+    dc.thresh = (uint32_t)(dropout_p * 65536.0f + 0.5f);
+    dc.scale = 1.0f / (1.0f - (float)dc.thresh / 65536.0f);
+    dc.seed = dropout_seed;
+    dc.site = dropout_site;
+  }
   switch (D / 128) {
 #define VS_LN_CASE(NV)                                                                                              \
   case NV:                                                                                                          \
-    if (dy_is_f32) ln_bwd_kernel<NV, true><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, dx_in, M, dx_out, db, dgamma, dbeta); \
-    else ln_bwd_kernel<NV, false><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, dx_in, M, dx_out, db, dgamma, dbeta);          \
+    if (dy_is_f32) ln_bwd_kernel<NV, true><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, dx_in, M, dx_out, db, dgamma, dbeta, dc); \
+    else ln_bwd_kernel<NV, false><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, dx_in, M, dx_out, db, dgamma, dbeta, dc);          \
     break;
     VS_LN_CASE(1) VS_LN_CASE(2) VS_LN_CASE(3) VS_LN_CASE(4) VS_LN_CASE(5) VS_LN_CASE(6) VS_LN_CASE(7) VS_LN_CASE(8)
 #undef VS_LN_CASE

@@ -313,6 +313,42 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ g, float* _
   }
 }
 
+// in-place hidden-state dropout on an fp32 [M, D] matrix (+ optional bf16 copy); pair-hash scheme of common.cuh.
+// Used for the embedding dropout (TF:126) forward and — same mask — on the gradient in backward.
+__global__ void dropout_rows_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ x16, long long n4,
+                                    const DropCfg drop) {
+  const uint32_t sd = drop_seed(drop);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    if (drop.thresh != 0u) {
+      bool k0, k1, k2, k3;
+      drop_keep2((uint32_t)(i * 4), sd, drop.thresh, k0, k1);
+      drop_keep2((uint32_t)(i * 4 + 2), sd, drop.thresh, k2, k3);
+      v.x = k0 ? v.x * drop.scale : 0.0f; v.y = k1 ? v.y * drop.scale : 0.0f;
+      v.z = k2 ? v.z * drop.scale : 0.0f; v.w = k3 ? v.w * drop.scale : 0.0f;
+      reinterpret_cast<float4*>(x)[i] = v;
+    }
+    if (x16) reinterpret_cast<uint2*>(x16)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// writes the keep mask (1/0 bytes) of a dropout site: scheme 0 = pair hash over a dense [n] index space (hidden
+// states), scheme 1 = per-element hash (attention probabilities).  Test / debugging aid.
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, long long n, int scheme, const DropCfg drop) {
+  const uint32_t sd = drop_seed(drop);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    bool keep;
+    if (scheme == 0) {
+      bool k0, k1;
+      drop_keep2((uint32_t)(i & ~1LL), sd, drop.thresh, k0, k1);
+      keep = (i & 1) ? k1 : k0;
+    } else {
+      keep = drop_keep((uint32_t)i, sd, drop.thresh);
+    }
+    out[i] = keep ? 1 : 0;
+  }
+}
+
 static inline int grid_for(long long total, int block, int nsm) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)nsm * 16;
@@ -463,6 +499,42 @@ extern "C" int vs_unpack_conv3x3_grad(const float* g, float* dw, int32_t O, int3
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_unpack_conv3x3_grad: no CUDA device");
   unpack_conv3x3_grad_kernel<<<grid_for((long long)O * I * 9, 256, nsm), 256, 0, (cudaStream_t)stream>>>(g, dw, O, I);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+static int make_drop_cfg(DropCfg* dc, float p, const uint32_t* seed, uint32_t site, const char* who) {
+  dc->thresh = 0u; dc->scale = 1.0f; dc->seed = nullptr; dc->site = 0u;
+  if (p > 0.0f) {
+    if (!(p < 1.0f) || seed == nullptr) { set_error("%s: need 0 < p < 1 and a device seed pointer", who); return -1; }
+    dc->thresh = (uint32_t)(p * 65536.0f + 0.5f);
+    dc->scale = 1.0f / (1.0f - (float)dc->thresh / 65536.0f);
+    dc->seed = seed;
+    dc->site = site;
+  }
+  return 0;
+}
+
+extern "C" int vs_dropout_rows(float* x, void* x_bf16, int64_t n, float dropout_p, const uint32_t* dropout_seed,
+                               uint32_t dropout_site, void* stream) {
+  VS_CHECK_ARG(x && n > 0 && n % 4 == 0 && n < (1LL << 32), "vs_dropout_rows: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_dropout_rows: no CUDA device");
+  DropCfg dc;
+  if (int rc = make_drop_cfg(&dc, dropout_p, dropout_seed, dropout_site, "vs_dropout_rows")) return rc;
+  dropout_rows_kernel<<<grid_for(n / 4, 256, nsm), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)x_bf16, n / 4, dc);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, float dropout_p, const uint32_t* dropout_seed,
+                               uint32_t dropout_site, void* stream) {
+  VS_CHECK_ARG(out && n > 0 && n < (1LL << 32) && (scheme == 0 || scheme == 1), "vs_dropout_mask: bad arguments");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_dropout_mask: no CUDA device");
+  DropCfg dc;
+  if (int rc = make_drop_cfg(&dc, dropout_p, dropout_seed, dropout_site, "vs_dropout_mask")) return rc;
+  dropout_mask_kernel<<<grid_for(n, 256, nsm), 256, 0, (cudaStream_t)stream>>>(out, n, scheme, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }

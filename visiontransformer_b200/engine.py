@@ -79,6 +79,8 @@ class Engine:
         self._ws: Dict = {}
         self._saved = None
         self.grad_ready_hook = None  # callable(bucket_name) used by the data-parallel wrapper
+        self.rng_step = None         # device uint32 counter: advances once per dropout-enabled forward (graph-safe)
+        self._drop = (0.0, 0.0)      # (hidden p, attention p) used by the last training forward
         self.launches = 0            # kernel launches issued by the last forward/backward (for bench bookkeeping)
 
     # ------------------------------------------------------------------------------------------ parameters
@@ -229,8 +231,17 @@ class Engine:
         return ws
 
     # ------------------------------------------------------------------------------------------ forward
-    def forward_lowres(self, x: torch.Tensor, train: bool) -> torch.Tensor:
-        """image fp32 [B,3,S,S] -> low-resolution logits fp32 [B,C,g,g] (seg_head output before the upsample)."""
+    def seed_dropout(self, seed: int) -> None:
+        """sets the per-step dropout counter (tests / reproducibility)."""
+        assert self.device is not None, "call after the module is on its CUDA device (ensure_packed)"
+        self.rng_step = torch.tensor([seed & 0x7FFFFFFF], device=self.device, dtype=torch.int32)
+
+    def _site(self, p: float, site: int):
+        return (p, self.rng_step, site) if p > 0.0 else None
+
+    def forward_lowres(self, x: torch.Tensor, train: bool, dropout: bool = False) -> torch.Tensor:
+        """image fp32 [B,3,S,S] -> low-resolution logits fp32 [B,C,g,g] (seg_head output before the upsample).
+        dropout=True applies hidden / attention dropout with the config's probabilities (module.training)."""
         cfg = self.cfg
         K.require_cuda(x, "ViTSegmentationModel.forward")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
@@ -249,6 +260,14 @@ class Engine:
         g, T1, M = ws["g"], ws["T1"], ws["M"]
         scale = 1.0 / math.sqrt(D // H)
         n = 0
+        p_hid = float(cfg.hidden_dropout_prob) if (dropout and train) else 0.0
+        p_att = float(cfg.attention_probs_dropout_prob) if (dropout and train) else 0.0
+        if p_hid > 0.0 or p_att > 0.0:
+            if self.rng_step is None or self.rng_step.device != x.device:
+                self.rng_step = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(x.device)
+            self.rng_step.add_(1)   # device-side: a captured graph advances it on every replay
+        if train:
+            self._drop = (p_hid, p_att)
 
         # --- embeddings: patch projection (+bias +pos) and CLS rows (TF:100-128)
         K.patchify(x, ws["patches"], P)
@@ -259,6 +278,9 @@ class Engine:
         K.cls_rows(self.w32("backbone.embeddings.cls_token"), self.w32("backbone.embeddings.position_embeddings"),
                    xcur, B, T1, D)
         n += 3
+        if p_hid > 0.0:   # embedding dropout (TF:126), site 0
+            K.dropout_rows(xcur, None, self._site(p_hid, 0))
+            n += 1
         # --- encoder layers (TF:328-346)
         for i in range(L):
             j = i if train else 0
@@ -271,16 +293,18 @@ class Engine:
                             LN_EPS, y_bf16=ws["ln1"][j], mean=st[0] if train else None, rstd=st[1] if train else None)
             wqkv, bqkv = self.fused_qkv(i)
             K.gemm(ws["ln1"][j], wqkv, ws["qkv"][j], bias=bqkv)
-            K.attention_fwd(ws["qkv"][j], ws["ctx"][j], ws["lse"][i] if train else None, B, T1, H, scale)
+            K.attention_fwd(ws["qkv"][j], ws["ctx"][j], ws["lse"][i] if train else None, B, T1, H, scale,
+                            dropout=self._site(p_att, 1000 + i))
             K.gemm(ws["ctx"][j], self.w16(p + "attention.output.dense.weight"), x_mid,
-                   bias=self.w32(p + "attention.output.dense.bias"), residual=x_in)
+                   bias=self.w32(p + "attention.output.dense.bias"), residual=x_in,
+                   dropout=self._site(p_hid, 1 + 2 * i))
             K.layernorm_fwd(x_mid, self.w32(p + "layernorm_after.weight"), self.w32(p + "layernorm_after.bias"),
                             LN_EPS, y_bf16=ws["ln2"][j], mean=st[2] if train else None, rstd=st[3] if train else None)
             K.gemm(ws["ln2"][j], self.w16(p + "intermediate.dense.weight"), ws["h_act"][j],
                    bias=self.w32(p + "intermediate.dense.bias"), act=K.ACT_GELU,
                    out2=ws["h_pre"][i] if train else None)
             K.gemm(ws["h_act"][j], self.w16(p + "output.dense.weight"), x_out,
-                   bias=self.w32(p + "output.dense.bias"), residual=x_mid)
+                   bias=self.w32(p + "output.dense.bias"), residual=x_mid, dropout=self._site(p_hid, 2 + 2 * i))
             n += 7
         x_fin = ws["x_in"][L] if train else ws["x_in"][0]
         fs = ws["fstats"] if train else None
@@ -338,6 +362,7 @@ class Engine:
         dlow = dlow.contiguous().to(F32)
         n = 0
         hook = self.grad_ready_hook
+        p_hid, p_att = self._drop
 
         # --- head
         K.conv1x1_bwd(dlow, ws["feat"], self.w32("seg_head.2.weight").view(Cn, HEAD_CH), ws["dfeat"],
@@ -351,8 +376,10 @@ class Engine:
         # final LayerNorm
         fs = ws["fstats"]
         dx, dx_other = ws["dx_a"], ws["dx_b"]
+        # the bf16 copy of dx feeds the backward GEMMs of the last layer's fc2, whose output was dropped out (site 2L)
         K.layernorm_bwd(ws["dtok"], ws["x_in"][L], self.w32("backbone.layernorm.weight"), fs[0], fs[1], None, dx,
-                        ws["dx16"], self.g32("backbone.layernorm.weight"), self.g32("backbone.layernorm.bias"))
+                        ws["dx16"], self.g32("backbone.layernorm.weight"), self.g32("backbone.layernorm.bias"),
+                        dropout=self._site(p_hid, 2 * L) if L > 0 else None)
         n += 8
         if hook:
             hook("head")
@@ -374,7 +401,7 @@ class Engine:
             # LN2 + skip
             K.layernorm_bwd(ws["d_ln"], ws["x_mid"][i], self.w32(p + "layernorm_after.weight"), st[2], st[3], dx,
                             dx_other, ws["dx16"], self.g32(p + "layernorm_after.weight"),
-                            self.g32(p + "layernorm_after.bias"))
+                            self.g32(p + "layernorm_after.bias"), dropout=self._site(p_hid, 1 + 2 * i))
             dx, dx_other = dx_other, dx
             # attention output projection
             K.colsum(ws["dx16"], self.g32(p + "attention.output.dense.bias"), accumulate=True)
@@ -383,7 +410,7 @@ class Engine:
             K.gemm(ws["dx16"], self.w16(p + "attention.output.dense.weight"), ws["dctx"], b_mn=True)
             # attention core
             K.attention_bwd(ws["qkv"][i], ws["ctx"][i], ws["dctx"], ws["lse"][i], ws["dqkv"], ws["dq_acc"], ws["delta"],
-                            B, T1, H, scale)
+                            B, T1, H, scale, dropout=self._site(p_att, 1000 + i))
             K.cast_bf16_rows(ws["dq_acc"], ws["dqkv"][:, :D])
             # fused QKV projection
             gw, gb = self.fused_qkv(i, arena="grads")
@@ -392,14 +419,19 @@ class Engine:
             K.gemm(ws["dqkv"], ws["ln1"][i], gw, a_mn=True, b_mn=True, accumulate=True)
             K.gemm(ws["dqkv"], wqkv, ws["d_ln"], b_mn=True)
             # LN1 + skip
+            # next consumer of dx16: fc2 of layer i-1 (site 2i); for i == 0 the embedding dropout is applied below
             K.layernorm_bwd(ws["d_ln"], ws["x_in"][i], self.w32(p + "layernorm_before.weight"), st[0], st[1], dx,
                             dx_other, ws["dx16"], self.g32(p + "layernorm_before.weight"),
-                            self.g32(p + "layernorm_before.bias"))
+                            self.g32(p + "layernorm_before.bias"),
+                            dropout=self._site(p_hid, 2 * i) if i > 0 else None)
             dx, dx_other = dx_other, dx
             n += 19
             if hook:
                 hook(f"layer{i}")
         # --- embeddings
+        if p_hid > 0.0:   # same mask as the forward embedding dropout, on the gradient (fp32 in place + bf16 copy)
+            K.dropout_rows(dx, ws["dx16"], self._site(p_hid, 0))
+            n += 1
         K.embed_bwd(dx, self.g32("backbone.embeddings.cls_token").view(D),
                     self.g32("backbone.embeddings.position_embeddings").view(T1 * D),
                     self.g32("backbone.embeddings.patch_embeddings.projection.bias"), B, T1, D)

@@ -58,7 +58,8 @@ def _rowmajor(t: torch.Tensor, what: str) -> int:
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=None, aux=None, aux_mode=AUX_NONE,
-         residual=None, row_tokens=0, accumulate=False, split_k=0, tile_cfg=0, M=None, N=None, K=None):
+         residual=None, row_tokens=0, accumulate=False, split_k=0, tile_cfg=0, M=None, N=None, K=None,
+         dropout=None):
     """out[M,N] = epilogue(sum_k A(m,k) B(n,k)); see include/vitseg.h:vs_gemm_desc.
 
     a: bf16 [M,K] (or [K,M] when a_mn); b: bf16 [N,K] (or [K,N] when b_mn); out: bf16 or fp32 2-D view."""
@@ -96,6 +97,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=Non
     d.row_tokens = row_tokens
     d.split_k = split_k
     d.tile_cfg = tile_cfg
+    if dropout is not None and dropout[0] > 0.0:   # (p, seed tensor (uint32/int32 device), site)
+        d.dropout_p, d.dropout_seed, d.dropout_site = dropout[0], ptr(dropout[1]), dropout[2]
     if _GEMM_TIMING:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -126,28 +129,50 @@ def layernorm_fwd(x, gamma, beta, eps, y_bf16=None, y_f32=None, mean=None, rstd=
                                       ptr(rstd), stream()), "vs_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_bf16, dgamma, dbeta):
+def _drop(dropout):
+    if dropout is None or dropout[0] <= 0.0:
+        return 0.0, None, 0
+    return float(dropout[0]), ptr(dropout[1]), int(dropout[2])
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_bf16, dgamma, dbeta, dropout=None):
     require_cuda(x, "layernorm_bwd")
     M, D = x.shape
     assert dy.is_contiguous() and dy.dtype in (BF16, F32)
     _count(1)
     check(_lib.load().vs_layernorm_bwd(ptr(dy), int(dy.dtype == F32), ptr(x), ptr(gamma), ptr(mean), ptr(rstd),
-                                      ptr(dx_in), M, D, ptr(dx_out), ptr(dx_bf16), ptr(dgamma), ptr(dbeta), stream()),
+                                      ptr(dx_in), M, D, ptr(dx_out), ptr(dx_bf16), ptr(dgamma), ptr(dbeta), *_drop(dropout),
+                                      stream()),
           "vs_layernorm_bwd")
 
 
-def attention_fwd(qkv, ctx, lse, B, N, H, scale):
+def attention_fwd(qkv, ctx, lse, B, N, H, scale, dropout=None):
     require_cuda(qkv, "attention_fwd")
     assert qkv.dtype == BF16 and qkv.is_contiguous() and ctx.is_contiguous()
     _count(1)
-    check(_lib.load().vs_attention_fwd(ptr(qkv), ptr(ctx), ptr(lse), B, N, H, scale, stream()), "vs_attention_fwd")
+    check(_lib.load().vs_attention_fwd(ptr(qkv), ptr(ctx), ptr(lse), B, N, H, scale, *_drop(dropout), stream()),
+          "vs_attention_fwd")
 
 
-def attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_accum, delta, B, N, H, scale):
+def attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_accum, delta, B, N, H, scale, dropout=None):
     require_cuda(qkv, "attention_bwd")
     _count(2)
     check(_lib.load().vs_attention_bwd(ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse), ptr(dqkv), ptr(dq_accum), ptr(delta), B,
-                                      N, H, scale, stream()), "vs_attention_bwd")
+                                      N, H, scale, *_drop(dropout), stream()), "vs_attention_bwd")
+
+
+def dropout_rows(x, x_bf16, dropout):
+    """in-place dropout of a contiguous fp32 tensor (+ optional bf16 copy); dropout = (p, seed tensor, site)."""
+    require_cuda(x, "dropout_rows")
+    assert x.dtype == F32 and x.is_contiguous()
+    _count(1)
+    check(_lib.load().vs_dropout_rows(ptr(x), ptr(x_bf16), x.numel(), *_drop(dropout), stream()), "vs_dropout_rows")
+
+
+def dropout_mask(out, scheme, dropout):
+    assert out.dtype == torch.uint8 and out.is_contiguous()
+    check(_lib.load().vs_dropout_mask(ptr(out), out.numel(), scheme, *_drop(dropout), stream()), "vs_dropout_mask")
+    return out
 
 
 def patchify(img, out, P):

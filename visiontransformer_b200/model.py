@@ -114,8 +114,8 @@ class _LowresFn(torch.autograd.Function):
     """image -> low-res logits; backward fills parameter gradients inside the engine (flat arena)."""
 
     @staticmethod
-    def forward(ctx, x, anchor, engine):
-        low = engine.forward_lowres(x, train=True)
+    def forward(ctx, x, anchor, engine, dropout):
+        low = engine.forward_lowres(x, train=True, dropout=dropout)
         engine._generation = getattr(engine, "_generation", 0) + 1
         ctx.engine = engine
         ctx.generation = engine._generation
@@ -128,7 +128,7 @@ class _LowresFn(torch.autograd.Function):
             raise RuntimeError("ViTSegmentationModel: activations of this forward were overwritten by a later forward; "
                                "call backward() before the next training-mode forward")
         eng.backward_lowres(dlow)
-        return None, None, None
+        return None, None, None, None
 
 
 class _UpsampleFn(torch.autograd.Function):
@@ -205,7 +205,7 @@ class ViTSegmentationModel(nn.Module):
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             anchor = self.seg_head[2].bias
-            return _LowresFn.apply(x, anchor, self._engine)
+            return _LowresFn.apply(x, anchor, self._engine, self._dropout_active())
         return self._engine.forward_lowres(x, train=False)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
