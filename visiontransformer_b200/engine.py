@@ -233,7 +233,8 @@ class Engine:
     # ------------------------------------------------------------------------------------------ forward
     def seed_dropout(self, seed: int) -> None:
         """sets the per-step dropout counter (tests / reproducibility)."""
-        assert self.device is not None, "call after the module is on its CUDA device (ensure_packed)"
+        if self.device is None:
+            self.ensure_packed(next(self.module.parameters()).device)
         self.rng_step = torch.tensor([seed & 0x7FFFFFFF], device=self.device, dtype=torch.int32)
 
     def _site(self, p: float, site: int):
