@@ -339,7 +339,14 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators captured into the CUDA graph: tear down explicitly and leave without the
+        # process-group destructor (it can wait forever on the captured work objects)
+        del graphed
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
