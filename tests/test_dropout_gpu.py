@@ -222,4 +222,6 @@ def test_training_step_with_dropout_matches_masked_reference():
             continue
         g = named["model." + k].grad
         assert g is not None, k
-        assert _rel(g.cpu(), v.grad) < 4e-2, (k, _rel(g.cpu(), v.grad))
+        # key biases have an exactly-zero true gradient (softmax shift invariance): absolute floor for such tensors
+        err = (g.cpu() - v.grad).abs().max().item()
+        assert err <= 4e-2 * v.grad.abs().max().item() + 2e-5, (k, err, v.grad.abs().max().item())
