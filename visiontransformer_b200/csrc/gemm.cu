@@ -24,7 +24,7 @@ namespace vs {
 
 constexpr int BM = 128;  // rows of A per CTA
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;  // 4 per TMEM lane quadrant = 4 per SM sub-partition: the epilogue is latency-bound
 constexpr int kThreads = 128 + kEpiWarps * 32;
 
 struct GemmParams {
@@ -53,7 +53,7 @@ struct Cfg {
   static constexpr int kABytes = BM * BK * 2;                    // 16 KB
   static constexpr int kBAlloc = kBBoxes * 64 * BK * 2;          // smem reserved for B per stage
   static constexpr int kStageBytes = kABytes + kBAlloc;
-  static constexpr int kEpiBytes = kEpiWarps * 4096;             // one swizzled 32x32 fp32 staging tile per warp
+  static constexpr int kEpiBytes = kEpiWarps * 2048;             // one swizzled 32x16 fp32 staging tile per warp
   static constexpr int kStages = (222 * 1024 - kEpiBytes) / kStageBytes > 8 ? 8 : (222 * 1024 - kEpiBytes) / kStageBytes;
   static constexpr int kEpiOffset = kStages * kStageBytes;
   static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
@@ -128,55 +128,39 @@ __device__ __forceinline__ float aux_fn(int mode, float v, float x) {
   return mode == 1 ? v * gelu_erf_grad(x) : (x > 0.0f ? v : 0.0f);
 }
 
-// One warp's epilogue for one tile: kChunks chunks of 32 rows x 32 columns.
-//   * accumulators: tcgen05.ld (thread = row) -> swizzled smem transpose -> coalesced layout
-//       fp32 output : lane <-> 4 columns, 4 rows per request (8 iterations per chunk)
-//       bf16 output : lane <-> 8 columns, 8 rows per request (4 iterations per chunk)
-//   * software pipeline: bias for all chunks and the first chunk's residual / aux tile are requested BEFORE waiting for
-//     the accumulator; while chunk c is processed, the tcgen05.ld and the global loads of chunk c+1 are in flight.
-//     (ncu r01: the epilogue warps sat ~80 % of their time on long-scoreboard waits for tcgen05.ld and bias loads;
-//     with K = 768 the epilogue, not the MMA main loop, set the tile time.)
-template <int kChunks, bool OUT_F32>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint8_t* stg, uint32_t tmem_addr, uint64_t* tfull,
-                                              uint32_t tfull_phase, int row0, int col0, bool first_split, int lane) {
-  constexpr int CPL = OUT_F32 ? 4 : 8;        // columns per lane
-  constexpr int LPR = 32 / CPL;               // lanes per row
-  constexpr int RPI = 32 / LPR;               // rows per iteration (request)
-  constexpr int NIT = 32 / RPI;               // iterations per chunk
-  const int cl = lane % LPR;
-  const int rsub = lane / LPR;
+// One warp's epilogue for one tile: kChunks chunks of 32 rows x 16 columns (fp32 output).
+//   * accumulators: tcgen05.ld.x16 (thread = row) -> swizzled smem transpose -> lane <-> 4 columns, 8 rows per request,
+//     so every global access (bias, residual, out) is a full-sector row-contiguous request
+//   * software pipeline: bias for all chunks and the first chunk's residual tile are requested BEFORE waiting for the
+//     accumulator; while chunk c is processed, the tcgen05.ld and the residual loads of chunk c+1 are in flight.
+// 16 epilogue warps (4 per sub-partition): ncu r01b showed the 8-warp epilogue issue-starved (IPC 0.28, stalls =
+// long scoreboard + fixed-latency waits) and, at K = 768, longer than the MMA main loop.
+template <int kChunks>
+__device__ __forceinline__ void epilogue_tile_f32(const GemmParams& p, uint8_t* stg, uint32_t tmem_addr, uint64_t* tfull,
+                                                  uint32_t tfull_phase, int row0, int col0, bool first_split, int lane) {
+  const int cq = lane & 3;            // column quad within the 16-column chunk
+  const int rsub = lane >> 2;         // row within each group of 8 rows
   const int r0 = row0 + rsub;
   const bool use_bias = p.bias != nullptr && first_split;
-  const bool use_res = OUT_F32 && p.residual != nullptr && first_split;
-  const bool use_aux = !OUT_F32 && p.aux_mode != 0;
+  const bool use_res = p.residual != nullptr && first_split;
 
-  float4 bias_r[kChunks][CPL / 4];
+  float4 bias_r[kChunks];
 #pragma unroll
-  for (int c = 0; c < kChunks; ++c)
-#pragma unroll
-    for (int h = 0; h < CPL / 4; ++h) {
-      bias_r[c][h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int n = col0 + c * 32 + cl * CPL + 4 * h;
-      if (use_bias && n < p.N) bias_r[c][h] = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    }
-
-  float4 res_r[2][OUT_F32 ? NIT : 1];
-  uint4 aux_r[2][OUT_F32 ? 1 : NIT];
+  for (int c = 0; c < kChunks; ++c) {
+    bias_r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = col0 + c * 16 + cq * 4;
+    if (use_bias && n < p.N) bias_r[c] = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  }
+  float4 res_r[2][4];
   auto prefetch = [&](int c, int buf) {
-    const int n = col0 + c * 32 + cl * CPL;
+    const int n = col0 + c * 16 + cq * 4;
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int r = r0 + RPI * i;
-      const bool ok = r < p.M && n < p.N;
-      if (OUT_F32) {
-        res_r[buf][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (use_res && ok) {
-          const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
-          res_r[buf][i] = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
-        }
-      } else {
-        aux_r[buf][i] = make_uint4(0u, 0u, 0u, 0u);
-        if (use_aux && ok) aux_r[buf][i] = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)r * p.ldaux + n));
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 8 * i;
+      res_r[buf][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (use_res && r < p.M && n < p.N) {
+        const long long rrow = (p.row_tokens > 0) ? (r % p.row_tokens) : r;
+        res_r[buf][i] = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + n);
       }
     }
   };
@@ -184,77 +168,51 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint8_t* stg,
 
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
-  uint32_t v[32];
-  tmem_ld32(tmem_addr, v);
+  uint32_t v[16];
+  tmem_ld16(tmem_addr, v);
+  const uint32_t dseed = p.drop.thresh != 0u ? drop_seed(p.drop) : 0u;
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) {
-    const int nb = col0 + c * 32;
+    const int nb = col0 + c * 16;
     tmem_ld_wait();
-    // transpose through smem (16-byte slots XOR-swizzled by row: conflict-free both ways)
+    // rows are 64 B apart in the staging tile; 16-byte slots XOR-swizzled by (row >> 1): conflict-free both ways
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
           make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    if (c + 1 < kChunks) tmem_ld32(tmem_addr + (c + 1) * 32, v);   // in flight while this chunk is processed
+    if (c + 1 < kChunks) tmem_ld16(tmem_addr + (c + 1) * 16, v);   // in flight while this chunk is processed
     __syncwarp();
     if (c + 1 < kChunks) prefetch(c + 1, (c + 1) & 1);
     if (nb < p.N) {
-      const int n = nb + cl * CPL;
+      const int n = nb + cq * 4;
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int rl = rsub + RPI * i;
-        const int r = r0 + RPI * i;
-        float f[CPL];
-#pragma unroll
-        for (int h = 0; h < CPL / 4; ++h) {
-          const int slot = cl * (CPL / 4) + h;
-          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((slot ^ (rl & 7)) << 4));
-          f[4 * h + 0] = a.x + bias_r[c][h].x; f[4 * h + 1] = a.y + bias_r[c][h].y;
-          f[4 * h + 2] = a.z + bias_r[c][h].z; f[4 * h + 3] = a.w + bias_r[c][h].w;
-        }
+      for (int i = 0; i < 4; ++i) {
+        const int rl = rsub + 8 * i;
+        const int r = r0 + 8 * i;
+        float4 a = *reinterpret_cast<const float4*>(stg + rl * 64 + ((cq ^ ((rl >> 1) & 3)) << 4));
         if (r < p.M) {
-          if (OUT_F32) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) f[k] = act_fn(p.act, f[k]);
-            if (p.drop.thresh != 0u) {   // TF:267 / TF:310: dropout(dense(x)) then + residual
-              const uint32_t sd = drop_seed(p.drop);
-              const uint32_t e = (uint32_t)r * (uint32_t)p.N + (uint32_t)n;
-              bool k0, k1, k2, k3;
-              drop_keep2(e, sd, p.drop.thresh, k0, k1);
-              drop_keep2(e + 2, sd, p.drop.thresh, k2, k3);
-              f[0] = k0 ? f[0] * p.drop.scale : 0.0f; f[1] = k1 ? f[1] * p.drop.scale : 0.0f;
-              f[2] = k2 ? f[2] * p.drop.scale : 0.0f; f[3] = k3 ? f[3] * p.drop.scale : 0.0f;
-            }
-            const float4 rr = res_r[c & 1][i];
-            const float4 o4 = make_float4(f[0] + rr.x, f[1] + rr.y, f[2] + rr.z, f[3] + rr.w);
-            float* o = reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + n;
-            if (p.accumulate) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(o4.x), "f"(o4.y), "f"(o4.z),
-                           "f"(o4.w)
-                           : "memory");
-            } else {
-              *reinterpret_cast<float4*>(o) = o4;
-            }
+          a.x += bias_r[c].x; a.y += bias_r[c].y; a.z += bias_r[c].z; a.w += bias_r[c].w;
+          if (p.act == 1) {
+            a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+          } else if (p.act == 2) {
+            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+          }
+          if (p.drop.thresh != 0u) {   // TF:267 / TF:310: dropout(dense(x)) then + residual
+            const uint32_t e = (uint32_t)r * (uint32_t)p.N + (uint32_t)n;
+            bool k0, k1, k2, k3;
+            drop_keep2(e, dseed, p.drop.thresh, k0, k1);
+            drop_keep2(e + 2, dseed, p.drop.thresh, k2, k3);
+            a.x = k0 ? a.x * p.drop.scale : 0.0f; a.y = k1 ? a.y * p.drop.scale : 0.0f;
+            a.z = k2 ? a.z * p.drop.scale : 0.0f; a.w = k3 ? a.w * p.drop.scale : 0.0f;
+          }
+          const float4 rr = res_r[c & 1][i];
+          a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+          float* o = reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + n;
+          if (p.accumulate) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                         : "memory");
           } else {
-            if (p.out2 != nullptr)
-              *reinterpret_cast<uint4*>(p.out2 + (long long)r * p.ldo2 + n) =
-                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-            if (p.act != 0) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] = act_fn(p.act, f[k]);
-            }
-            if (use_aux) {
-              const uint4 a = aux_r[c & 1][i];
-              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 x = unpack_bf16(aw[k]);
-                f[2 * k] = aux_fn(p.aux_mode, f[2 * k], x.x);
-                f[2 * k + 1] = aux_fn(p.aux_mode, f[2 * k + 1], x.y);
-              }
-            }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n) =
-                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            *reinterpret_cast<float4*>(o) = a;
           }
         }
       }
@@ -263,70 +221,96 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint8_t* stg,
   }
 }
 
-// bf16-output epilogue, one output row per thread straight from the tcgen05.ld registers (no smem staging).
-// Measured faster than the transposed form for 2-byte outputs: its extra shared-memory traffic (4 KB in + 4 KB out
-// per chunk) competes with the UMMA operand reads and TMA writes that already saturate the smem port in the main loop.
+// bf16-output epilogue, one output row per thread straight from the tcgen05.ld registers (no smem staging: for
+// 2-byte outputs the transposed form was measured slower — its shared-memory traffic competes with the UMMA operand
+// reads and TMA writes of the main loop).  16-column chunks: each thread writes one full 32-byte sector per chunk.
 template <int kChunks>
-__device__ __forceinline__ void epilogue_tile_rows(const GemmParams& p, uint32_t tmem_addr, uint64_t* tfull,
+__device__ __forceinline__ void epilogue_tile_bf16(const GemmParams& p, uint32_t tmem_addr, uint64_t* tfull,
                                                    uint32_t tfull_phase, int row0, int col0, bool first_split, int lane) {
   const int r = row0 + lane;
   const bool row_ok = r < p.M;
   const bool add_bias = p.bias != nullptr && first_split;
+  // the first chunk's aux tile does not depend on the accumulator: request it before waiting
+  uint4 ax[2][2];
+  auto prefetch = [&](int c, int buf) {
+    const int n = col0 + c * 16;
+    ax[buf][0] = make_uint4(0u, 0u, 0u, 0u);
+    ax[buf][1] = make_uint4(0u, 0u, 0u, 0u);
+    if (p.aux_mode != 0 && row_ok && n < p.N) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (long long)r * p.ldaux + n);
+      ax[buf][0] = __ldg(a4);
+      ax[buf][1] = __ldg(a4 + 1);
+    }
+  };
+  prefetch(0, 0);
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
-#pragma unroll 1
+  uint32_t v[16];
+  tmem_ld16(tmem_addr, v);
+#pragma unroll
   for (int c = 0; c < kChunks; ++c) {
-    const int n = col0 + c * 32;
-    if (n >= p.N) break;  // warp-uniform
-    uint32_t v[32];
-    tmem_ld32(tmem_addr + c * 32, v);
-    uint4 ax[4];
-    if (p.aux_mode != 0 && row_ok) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (long long)r * p.ldaux + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ax[j] = __ldg(a4 + j);
-    }
+    const int n = col0 + c * 16;
     tmem_ld_wait();
-    float f[32];
+    float f[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (add_bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
-        f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-      }
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    if (c + 1 < kChunks) {
+      tmem_ld16(tmem_addr + (c + 1) * 16, v);
+      prefetch(c + 1, (c + 1) & 1);
     }
-    if (row_ok) {
-      if (p.out2 != nullptr) {
-        uint4* o2 = reinterpret_cast<uint4*>(p.out2 + (long long)r * p.ldo2 + n);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          o2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-      }
-      if (p.act != 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fn(p.act, f[j]);
-      }
-      if (p.aux_mode != 0) {
+    if (n < p.N) {
+      if (add_bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t aw[4] = {ax[j].x, ax[j].y, ax[j].z, ax[j].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 x = unpack_bf16(aw[q]);
-            f[8 * j + 2 * q] = aux_fn(p.aux_mode, f[8 * j + 2 * q], x.x);
-            f[8 * j + 2 * q + 1] = aux_fn(p.aux_mode, f[8 * j + 2 * q + 1], x.y);
-          }
+          const float4 b = __ldg(b4 + j);
+          f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
         }
       }
-      uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n);
+      if (row_ok) {
+        if (p.out2 != nullptr) {
+          uint4* o2 = reinterpret_cast<uint4*>(p.out2 + (long long)r * p.ldo2 + n);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o4[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          for (int j = 0; j < 2; ++j)
+            o2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (p.aux_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t aw[4] = {ax[c & 1][j].x, ax[c & 1][j].y, ax[c & 1][j].z, ax[c & 1][j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 x = unpack_bf16(aw[q]);
+              f[8 * j + 2 * q] *= gelu_erf_grad(x.x);
+              f[8 * j + 2 * q + 1] *= gelu_erf_grad(x.y);
+            }
+          }
+        } else if (p.aux_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t aw[4] = {ax[c & 1][j].x, ax[c & 1][j].y, ax[c & 1][j].z, ax[c & 1][j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 x = unpack_bf16(aw[q]);
+              f[8 * j + 2 * q] = x.x > 0.0f ? f[8 * j + 2 * q] : 0.0f;
+              f[8 * j + 2 * q + 1] = x.y > 0.0f ? f[8 * j + 2 * q + 1] : 0.0f;
+            }
+          }
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          o4[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+      }
     }
   }
 }
@@ -478,10 +462,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ------------------------------------------------ epilogue (this CTA's 128 rows of the tile)
     const int ew = warp - 4;
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;             // which half of the BN columns
-    constexpr int kColsPerWarp = BN / 2;
-    constexpr int kChunks = kColsPerWarp / 32;
-    uint8_t* stg = smem + L::kEpiOffset + ew * 4096;
+    const int slice = ew >> 2;            // which quarter of the BN columns
+    constexpr int kColsPerWarp = BN / 4;
+    constexpr int kChunks = kColsPerWarp / 16;
+    uint8_t* stg = smem + L::kEpiOffset + ew * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = unit; w < total_work; w += nunits) {
@@ -489,12 +473,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int t = w - split * tiles;
       const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
       const int row0 = tm * (BM * kNCta) + rank * BM + quad * 32;
-      const int col0 = tn * BN + half * kColsPerWarp;
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + half * kColsPerWarp);
+      const int col0 = tn * BN + slice * kColsPerWarp;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + slice * kColsPerWarp);
       if (p.out_f32)
-        epilogue_tile<kChunks, true>(p, stg, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
+        epilogue_tile_f32<kChunks>(p, stg, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
       else
-        epilogue_tile_rows<kChunks>(p, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
+        epilogue_tile_bf16<kChunks>(p, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
