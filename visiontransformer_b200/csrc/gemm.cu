@@ -76,7 +76,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // relaxed: the accumulator hand-off is ordered by tcgen05.fence::before_thread_sync; a release here would make the
+  // warp wait for all its outstanding global stores (ncu r01b: MEMBAR.ALL.CTA + ERRBAR per tile per warp)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // pair-wide variants of the tcgen05 helpers
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
@@ -232,8 +237,16 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmParams& p, uint32_t
   const bool add_bias = p.bias != nullptr && first_split;
   // the first chunk's aux tile does not depend on the accumulator: request it before waiting
   uint4 ax[2][2];
+  float4 bs[2][4];
   auto prefetch = [&](int c, int buf) {
     const int n = col0 + c * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bs[buf][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add_bias && n < p.N) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bs[buf][j] = __ldg(b4 + j);
+    }
     ax[buf][0] = make_uint4(0u, 0u, 0u, 0u);
     ax[buf][1] = make_uint4(0u, 0u, 0u, 0u);
     if (p.aux_mode != 0 && row_ok && n < p.N) {
@@ -259,13 +272,10 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmParams& p, uint32_t
       prefetch(c + 1, (c + 1) & 1);
     }
     if (n < p.N) {
-      if (add_bias) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b = __ldg(b4 + j);
-          f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float4 b = bs[c & 1][j];
+        f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
       }
       if (row_ok) {
         if (p.out2 != nullptr) {
@@ -483,7 +493,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) {
         if (CTA2 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0);
-        else mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_relaxed(&tempty_bar[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
