@@ -78,6 +78,25 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.256).  One row per thread is the natural layout after tcgen05.ld, so a
+// warp request touches 32 different lines; the LSU then costs one wavefront per (line, instruction).  Moving 32 B
+// per instruction instead of 16 B halves the wavefronts per byte (gemm_epi_bench: the second bf16 output of fc1
+// cost +31 us, the GELU' aux read +24 us with 128-bit accesses).  Addresses must be 32-byte aligned.
+struct __align__(32) u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ void st_global_256(void* ptr, const u32x8& a) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]),
+               "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7])
+               : "memory");
+}
+__device__ __forceinline__ u32x8 ld_global_nc_256(const void* ptr) {
+  u32x8 a;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.v[0]), "=r"(a.v[1]), "=r"(a.v[2]), "=r"(a.v[3]), "=r"(a.v[4]), "=r"(a.v[5]), "=r"(a.v[6]),
+                 "=r"(a.v[7])
+               : "l"(ptr));
+  return a;
+}
+
 // exact-erf GELU (hidden_act="gelu", TF:290-299) and its derivative, fp32.
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level): 2 MUFU ops (rcp, ex2) + ~8 FMAs per
 // element instead of erff()'s ~30-instruction branchy path, which made the fc1 / fc2-dgrad GEMM epilogues slower

@@ -235,24 +235,20 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmParams& p, uint32_t
   const int r = row0 + lane;
   const bool row_ok = r < p.M;
   const bool add_bias = p.bias != nullptr && first_split;
-  // the first chunk's aux tile does not depend on the accumulator: request it before waiting
-  uint4 ax[2][2];
-  float4 bs[2][4];
+  // bias and aux of a chunk do not depend on the accumulator: chunk 0 is requested before waiting for it, chunk c+1
+  // while chunk c is processed.  All row-scattered accesses are 256-bit (one full sector per thread per instruction).
+  u32x8 ax[2];
+  u32x8 bs[2][2];
   auto prefetch = [&](int c, int buf) {
     const int n = col0 + c * 16;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bs[buf][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (add_bias && n < p.N) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bs[buf][j] = __ldg(b4 + j);
-    }
-    ax[buf][0] = make_uint4(0u, 0u, 0u, 0u);
-    ax[buf][1] = make_uint4(0u, 0u, 0u, 0u);
-    if (p.aux_mode != 0 && row_ok && n < p.N) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (long long)r * p.ldaux + n);
-      ax[buf][0] = __ldg(a4);
-      ax[buf][1] = __ldg(a4 + 1);
+    for (int j = 0; j < 8; ++j) { ax[buf].v[j] = 0u; bs[buf][0].v[j] = 0u; bs[buf][1].v[j] = 0u; }
+    if (n < p.N) {
+      if (add_bias) {
+        bs[buf][0] = ld_global_nc_256(p.bias + n);
+        bs[buf][1] = ld_global_nc_256(p.bias + n + 8);
+      }
+      if (p.aux_mode != 0 && row_ok) ax[buf] = ld_global_nc_256(p.aux + (long long)r * p.ldaux + n);
     }
   };
   prefetch(0, 0);
@@ -273,17 +269,16 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmParams& p, uint32_t
     }
     if (n < p.N) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 b = bs[c & 1][j];
-        f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+      for (int j = 0; j < 8; ++j) {
+        f[j] += __uint_as_float(bs[c & 1][0].v[j]);
+        f[8 + j] += __uint_as_float(bs[c & 1][1].v[j]);
       }
       if (row_ok) {
         if (p.out2 != nullptr) {
-          uint4* o2 = reinterpret_cast<uint4*>(p.out2 + (long long)r * p.ldo2 + n);
+          u32x8 o;
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            o2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+          st_global_256(p.out2 + (long long)r * p.ldo2 + n, o);
         }
         if (p.act == 1) {
 #pragma unroll
@@ -294,32 +289,23 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmParams& p, uint32_t
         }
         if (p.aux_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t aw[4] = {ax[c & 1][j].x, ax[c & 1][j].y, ax[c & 1][j].z, ax[c & 1][j].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 x = unpack_bf16(aw[q]);
-              f[8 * j + 2 * q] *= gelu_erf_grad(x.x);
-              f[8 * j + 2 * q + 1] *= gelu_erf_grad(x.y);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float2 x = unpack_bf16(ax[c & 1].v[j]);
+            f[2 * j] *= gelu_erf_grad(x.x);
+            f[2 * j + 1] *= gelu_erf_grad(x.y);
           }
         } else if (p.aux_mode == 2) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t aw[4] = {ax[c & 1][j].x, ax[c & 1][j].y, ax[c & 1][j].z, ax[c & 1][j].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 x = unpack_bf16(aw[q]);
-              f[8 * j + 2 * q] = x.x > 0.0f ? f[8 * j + 2 * q] : 0.0f;
-              f[8 * j + 2 * q + 1] = x.y > 0.0f ? f[8 * j + 2 * q + 1] : 0.0f;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float2 x = unpack_bf16(ax[c & 1].v[j]);
+            f[2 * j] = x.x > 0.0f ? f[2 * j] : 0.0f;
+            f[2 * j + 1] = x.y > 0.0f ? f[2 * j + 1] : 0.0f;
           }
         }
-        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n);
+        u32x8 o;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          o4[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+        for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+        st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)r * p.ldo + n, o);
       }
     }
   }
@@ -589,11 +575,14 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   VS_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0, "vs_gemm_bf16: lda/ldb must be multiples of 8 elements");
   VS_CHECK_ARG(((uintptr_t)d->A % 16 == 0) && ((uintptr_t)d->B % 16 == 0) && ((uintptr_t)d->out % 16 == 0),
                "vs_gemm_bf16: operands must be 16-byte aligned");
-  VS_CHECK_ARG(d->ldo % (d->out_dtype ? 4 : 8) == 0, "vs_gemm_bf16: ldo alignment");
+  VS_CHECK_ARG(d->ldo % (d->out_dtype ? 4 : 16) == 0, "vs_gemm_bf16: ldo alignment (bf16 rows must be 32-byte multiples)");
+  VS_CHECK_ARG(d->out_dtype == 1 || (uintptr_t)d->out % 32 == 0, "vs_gemm_bf16: bf16 output must be 32-byte aligned");
+  VS_CHECK_ARG(d->bias == nullptr || (uintptr_t)d->bias % 32 == 0, "vs_gemm_bf16: bias must be 32-byte aligned");
   VS_CHECK_ARG(!d->accumulate || d->out_dtype == 1, "vs_gemm_bf16: accumulate requires fp32 output");
   VS_CHECK_ARG(d->act >= 0 && d->act <= 2 && d->aux_mode >= 0 && d->aux_mode <= 2, "vs_gemm_bf16: bad act/aux_mode");
-  VS_CHECK_ARG(d->aux_mode == 0 || (d->aux != nullptr && d->ldaux % 8 == 0), "vs_gemm_bf16: aux missing/misaligned");
-  VS_CHECK_ARG(d->out2 == nullptr || d->ldo2 % 8 == 0, "vs_gemm_bf16: ldo2 alignment");
+  VS_CHECK_ARG(d->aux_mode == 0 || (d->aux != nullptr && d->ldaux % 16 == 0 && (uintptr_t)d->aux % 32 == 0),
+               "vs_gemm_bf16: aux missing/misaligned (32-byte rows)");
+  VS_CHECK_ARG(d->out2 == nullptr || (d->ldo2 % 16 == 0 && (uintptr_t)d->out2 % 32 == 0), "vs_gemm_bf16: out2 alignment");
   VS_CHECK_ARG(d->residual == nullptr || d->ldr % 4 == 0, "vs_gemm_bf16: ldr alignment");
   VS_CHECK_ARG(d->split_k <= 1 || d->accumulate, "vs_gemm_bf16: split_k > 1 requires accumulate");
 
