@@ -89,54 +89,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
   if (warp == 4) {
-    if (lane == 0) {
-      uint8_t* sQ = smem + AttnFwdSmem::kQ;
-      uint8_t* sK = smem + AttnFwdSmem::kK;
-      uint8_t* sV = smem + AttnFwdSmem::kV;
-      uint8_t* sP = smem + AttnFwdSmem::kP;
+    // control warp: converged, the elected lane issues TMA / MMA (keeps descriptors in uniform registers)
+    uint8_t* sQ = smem + AttnFwdSmem::kQ;
+    uint8_t* sK = smem + AttnFwdSmem::kK;
+    uint8_t* sV = smem + AttnFwdSmem::kV;
+    uint8_t* sP = smem + AttnFwdSmem::kP;
+    if (elect_one()) {
       mbar_expect_tx(bar_k, 2 * 16384);
       tma_load_3d(sQ, &tmap_qkv, bar_k, h * kDH, q0, b);
       tma_load_3d(sK, &tmap_qkv, bar_k, D + h * kDH, 0, b);
       mbar_expect_tx(bar_v, 16384);
       tma_load_3d(sV, &tmap_qkv, bar_v, 2 * D + h * kDH, 0, b);
-      for (int j = 0; j < nblk; ++j) {
-        const uint32_t ph = j & 1;
-        const int kv0 = j * kBKV;
-        const int ncols = min(kBKV, ((N - kv0) + 15) & ~15);
-        mbar_wait(bar_k, ph);
-        tc_fence_after();
-        {
-          const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
-          const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-          const uint64_t bd = umma_desc_sw128(smem_u32(sK), 16, 1024);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv0 = j * kBKV;
+      const int ncols = min(kBKV, ((N - kv0) + 15) & ~15);
+      mbar_wait(bar_k, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
+        const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t bd = umma_desc_sw128(smem_u32(sK), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc, k > 0);
-          umma_commit(bar_s);
-        }
-        // K_j is free once S is complete: prefetch K_{j+1}
-        mbar_wait(bar_s, ph);
-        if (j + 1 < nblk) {
-          mbar_expect_tx(bar_k, 16384);
-          tma_load_3d(sK, &tmap_qkv, bar_k, D + h * kDH, kv0 + kBKV, b);
-        }
-        mbar_wait(bar_p, ph);
-        mbar_wait(bar_v, ph);
-        tc_fence_after();
-        {
-          const uint32_t idesc = umma_idesc_bf16(kBQ, kDH, 0, 1);
-          for (int kk = 0; kk < ncols / 16; ++kk) {
-            const uint64_t ad = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-            const uint64_t bd = umma_desc_sw128(smem_u32(sV) + kk * 2048, 16384, 1024);
-            umma_bf16(tmem_o, ad, bd, idesc, kk > 0);
-          }
-          umma_commit(bar_o);
-        }
-        mbar_wait(bar_o, ph);
-        if (j + 1 < nblk) {
-          mbar_expect_tx(bar_v, 16384);
-          tma_load_3d(sV, &tmap_qkv, bar_v, 2 * D + h * kDH, kv0 + kBKV, b);
-        }
+        for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc, k > 0);
+        umma_commit(bar_s);
       }
+      __syncwarp();
+      // K_j is free once S is complete: prefetch K_{j+1}
+      mbar_wait(bar_s, ph);
+      if (j + 1 < nblk && elect_one()) {
+        mbar_expect_tx(bar_k, 16384);
+        tma_load_3d(sK, &tmap_qkv, bar_k, D + h * kDH, kv0 + kBKV, b);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, ph);
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_bf16(kBQ, kDH, 0, 1);
+        for (int kk = 0; kk < ncols / 16; ++kk) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(smem_u32(sV) + kk * 2048, 16384, 1024);
+          umma_bf16(tmem_o, ad, bd, idesc, kk > 0);
+        }
+        umma_commit(bar_o);
+      }
+      __syncwarp();
+      mbar_wait(bar_o, ph);
+      if (j + 1 < nblk && elect_one()) {
+        mbar_expect_tx(bar_v, 16384);
+        tma_load_3d(sV, &tmap_qkv, bar_v, 2 * D + h * kDH, kv0 + kBKV, b);
+      }
+      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- softmax warps
@@ -208,13 +214,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     }
     if (q < N) {
       const float inv = 1.0f / l_run;
-      uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)b * N + q) * D + h * kDH);
+      __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        dst[i] = make_uint4(pack_bf16(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv),
-                            pack_bf16(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv),
-                            pack_bf16(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv),
-                            pack_bf16(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv));
+      for (int i = 0; i < 4; ++i) {
+        u32x8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16(o_acc[16 * i + 2 * j] * inv, o_acc[16 * i + 2 * j + 1] * inv);
+        st_global_256(dst + 16 * i, o);
+      }
       if (lse != nullptr) lse[((size_t)b * H + h) * N + q] = (m_run + log2f(l_run)) * kLn2;
     }
   }
@@ -226,26 +233,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 // ================================================================================================
 // backward
 // ================================================================================================
-// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]; one warp per (b,n,h) row of 64
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, int B, int N, int H) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long rows = (long long)B * N * H;
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const uint32_t a = reinterpret_cast<const uint32_t*>(o + row * kDH)[lane];
-  const uint32_t g = reinterpret_cast<const uint32_t*>(dout + row * kDH)[lane];
-  const float2 af = unpack_bf16(a), gf = unpack_bf16(g);
-  float s = warp_sum(af.x * gf.x + af.y * gf.y);
-  if (lane == 0) {
-    const int hh = int(row % H);
-    const long long bn = row / H;
-    const int n = int(bn % N);
-    const int bb = int(bn / N);
-    delta[((size_t)bb * H + hh) * N + n] = s;
-  }
-}
-
 struct AttnBwdSmem {
   static constexpr int kK = 0;
   static constexpr int kV = 16384;
@@ -257,10 +244,17 @@ struct AttnBwdSmem {
   static constexpr int kTotal = kBar + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(160, 1)
+// 8 compute warps: warp w owns TMEM lane quadrant (w & 3) and key-column half (w >> 2) of the 128x128 S / dP tiles,
+// so the exp / dS phase (the serialised part of the CTA) takes half as long as with one thread per query row.
+// delta_i = sum_d dO_i,d O_i,d is computed in the kernel (each thread reads its query row of O and dO straight from
+// global while the MMAs run) — no separate pre-pass over ctx / dctx.
+constexpr int kBwdThreads = 288;
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                float* __restrict__ dq_accum, int B, int N, int H, float scale, const DropCfg drop) {
+                const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
+                const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_accum, int B,
+                int N, int H, float scale, const DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBar);
@@ -278,14 +272,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const int nvalid_kv = min(kBKV, N - kv0);
   const int ncols = (nvalid_kv + 15) & ~15;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_qkv);
       tma_prefetch_desc(&tmap_do);
       mbar_init(bar_kv, 1);
       mbar_init(bar_q, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_pds, 128);
+      mbar_init(bar_pds, 256);
       mbar_init(bar_dq, 1);
       fence_mbar_init();
     }
@@ -299,75 +293,82 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
                  tm_dq = tmem_base + 384;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      uint8_t* sK = smem + AttnBwdSmem::kK;
-      uint8_t* sV = smem + AttnBwdSmem::kV;
-      uint8_t* sQ = smem + AttnBwdSmem::kQ;
-      uint8_t* sDO = smem + AttnBwdSmem::kDO;
-      const uint32_t aP = smem_u32(smem + AttnBwdSmem::kP);
-      const uint32_t aDS = smem_u32(smem + AttnBwdSmem::kDS);
+  if (warp == 8) {
+    // ---------------------------------------------------------------- control warp (converged; elected lane issues)
+    uint8_t* sK = smem + AttnBwdSmem::kK;
+    uint8_t* sV = smem + AttnBwdSmem::kV;
+    uint8_t* sQ = smem + AttnBwdSmem::kQ;
+    uint8_t* sDO = smem + AttnBwdSmem::kDO;
+    const uint32_t aP = smem_u32(smem + AttnBwdSmem::kP);
+    const uint32_t aDS = smem_u32(smem + AttnBwdSmem::kDS);
+    if (elect_one()) {
       mbar_expect_tx(bar_kv, 2 * 16384);
       tma_load_3d(sK, &tmap_qkv, bar_kv, D + h * kDH, kv0, b);
       tma_load_3d(sV, &tmap_qkv, bar_kv, 2 * D + h * kDH, kv0, b);
       mbar_expect_tx(bar_q, 2 * 16384);
       tma_load_3d(sQ, &tmap_qkv, bar_q, h * kDH, 0, b);
       tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, 0, b);
-      mbar_wait(bar_kv, 0);
-      for (int i = 0; i < nq; ++i) {
-        const uint32_t ph = i & 1;
-        mbar_wait(bar_q, ph);
-        tc_fence_after();
-        {
-          // S = Q K^T and dP = dO V^T, both [128 q x ncols kv], reduction over head_dim
-          const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
-          const uint64_t qd = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-          const uint64_t kd = umma_desc_sw128(smem_u32(sK), 16, 1024);
-          const uint64_t od = umma_desc_sw128(smem_u32(sDO), 16, 1024);
-          const uint64_t vd = umma_desc_sw128(smem_u32(sV), 16, 1024);
+    }
+    __syncwarp();
+    mbar_wait(bar_kv, 0);
+    for (int i = 0; i < nq; ++i) {
+      const uint32_t ph = i & 1;
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        // S = Q K^T and dP = dO V^T, both [128 q x ncols kv], reduction over head_dim
+        const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
+        const uint64_t qd = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t kd = umma_desc_sw128(smem_u32(sK), 16, 1024);
+        const uint64_t od = umma_desc_sw128(smem_u32(sDO), 16, 1024);
+        const uint64_t vd = umma_desc_sw128(smem_u32(sV), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
+        for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
 #pragma unroll
-          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
-          umma_commit(bar_s);
-        }
-        mbar_wait(bar_pds, ph);
-        tc_fence_after();
-        {
-          // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 128 keys, K = 128 queries)
-          const uint32_t idesc = umma_idesc_bf16(kBKV, kDH, 1, 1);
-#pragma unroll
-          for (int kk = 0; kk < kBQ / 16; ++kk) {
-            const uint64_t pd = umma_desc_sw128(aP + kk * 2048, 16384, 1024);
-            const uint64_t dod = umma_desc_sw128(smem_u32(sDO) + kk * 2048, 16384, 1024);
-            umma_bf16(tm_dv, pd, dod, idesc, (i > 0 || kk > 0));
-          }
-#pragma unroll
-          for (int kk = 0; kk < kBQ / 16; ++kk) {
-            const uint64_t dsd = umma_desc_sw128(aDS + kk * 2048, 16384, 1024);
-            const uint64_t qd = umma_desc_sw128(smem_u32(sQ) + kk * 2048, 16384, 1024);
-            umma_bf16(tm_dk, dsd, qd, idesc, (i > 0 || kk > 0));
-          }
-          // dQ_i = dS K : A = dS K-major (M = 128 queries, K = ncols keys), B = K MN-major (N = 64, K = keys)
-          const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
-          for (int kk = 0; kk < ncols / 16; ++kk) {
-            const uint64_t dsd = umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-            const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
-            umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
-          }
-          umma_commit(bar_dq);
-        }
-        mbar_wait(bar_dq, ph);
-        if (i + 1 < nq) {
-          mbar_expect_tx(bar_q, 2 * 16384);
-          tma_load_3d(sQ, &tmap_qkv, bar_q, h * kDH, (i + 1) * kBQ, b);
-          tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, (i + 1) * kBQ, b);
-        }
+        for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
+        umma_commit(bar_s);
       }
+      __syncwarp();
+      mbar_wait(bar_pds, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 128 keys, K = 128 queries)
+        const uint32_t idesc = umma_idesc_bf16(kBKV, kDH, 1, 1);
+#pragma unroll
+        for (int kk = 0; kk < kBQ / 16; ++kk) {
+          const uint64_t pd = umma_desc_sw128(aP + kk * 2048, 16384, 1024);
+          const uint64_t dod = umma_desc_sw128(smem_u32(sDO) + kk * 2048, 16384, 1024);
+          umma_bf16(tm_dv, pd, dod, idesc, (i > 0 || kk > 0));
+        }
+#pragma unroll
+        for (int kk = 0; kk < kBQ / 16; ++kk) {
+          const uint64_t dsd = umma_desc_sw128(aDS + kk * 2048, 16384, 1024);
+          const uint64_t qd = umma_desc_sw128(smem_u32(sQ) + kk * 2048, 16384, 1024);
+          umma_bf16(tm_dk, dsd, qd, idesc, (i > 0 || kk > 0));
+        }
+        // dQ_i = dS K : A = dS K-major (M = 128 queries, K = ncols keys), B = K MN-major (N = 64, K = keys)
+        const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
+        for (int kk = 0; kk < ncols / 16; ++kk) {
+          const uint64_t dsd = umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
+          umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
+        }
+        umma_commit(bar_dq);
+      }
+      __syncwarp();
+      mbar_wait(bar_dq, ph);
+      if (i + 1 < nq && elect_one()) {
+        mbar_expect_tx(bar_q, 2 * 16384);
+        tma_load_3d(sQ, &tmap_qkv, bar_q, h * kDH, (i + 1) * kBQ, b);
+        tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, (i + 1) * kBQ, b);
+      }
+      __syncwarp();
     }
   } else {
-    const int r = warp * 32 + lane;
-    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    // ---------------------------------------------------------------- compute warps
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = uint32_t(quad * 32) << 16;
     uint8_t* sP = smem + AttnBwdSmem::kP;
     uint8_t* sDS = smem + AttnBwdSmem::kDS;
     const float sl2 = scale * kLog2e;
@@ -375,16 +376,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     for (int i = 0; i < nq; ++i) {
       const uint32_t ph = i & 1;
       const int q = i * kBQ + r;
-      const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)N;
       const bool q_ok = q < N;
+      const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)N;
       float lse2 = 0.0f, dlt = 0.0f;
       if (q_ok) {
         lse2 = lse[((size_t)b * H + h) * N + q] * kLog2e;
-        dlt = delta[((size_t)b * H + h) * N + q];
+        // delta = rowsum(dO * O) over the 64 head dims, in fp32 from the bf16 rows
+        const size_t off = ((size_t)b * N + q) * D + h * kDH;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const u32x8 ov = ld_global_nc_256(ctx + off + 16 * k);
+          const u32x8 gv = ld_global_nc_256(dctx + off + 16 * k);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 a = unpack_bf16(ov.v[j]), g = unpack_bf16(gv.v[j]);
+            dlt = fmaf(a.x, g.x, dlt);
+            dlt = fmaf(a.y, g.y, dlt);
+          }
+        }
       }
       mbar_wait(bar_s, ph);
       tc_fence_after();
-      for (int c = 0; c < kBKV; c += 32) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 64 + cc * 32;
         float pf[32], dsf[32];
         if (c < ncols) {
           uint32_t sv[32], dv[32];
@@ -417,13 +432,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_arrive(bar_pds);
       mbar_wait(bar_dq, ph);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kDH; c += 32) {
+      {
+        // dQ partial of this key block: this thread owns head dims [32*half, +32) of query row q
         uint32_t v[32];
-        tmem_ld32(tm_dq + lane_off + c, v);
+        tmem_ld32(tm_dq + lane_off + half * 32, v);
         tmem_ld_wait();
         if (q_ok) {
-          float* dst = dq_accum + ((size_t)b * N + q) * D + h * kDH + c;
+          float* dst = dq_accum + ((size_t)b * N + q) * D + h * kDH + half * 32;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k),
@@ -434,32 +449,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
       tc_fence_before();
     }
-    // dK, dV rows: r <-> key kv0 + r.  All MMAs completed with the last bar_dq phase.
+    // dK (warps 0-3) and dV (warps 4-7): row r <-> key kv0 + r.  All MMAs completed with the last bar_dq phase.
     const int kv = kv0 + r;
+    const uint32_t src = half == 0 ? tm_dk : tm_dv;
+    __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (half == 0 ? D : 2 * D) + h * kDH;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t src = which == 0 ? tm_dk : tm_dv;
-      __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (which == 0 ? D : 2 * D) + h * kDH;
+    for (int c = 0; c < kDH; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(src + lane_off + c, v);
+      tmem_ld_wait();
+      if (kv < N) {
 #pragma unroll
-      for (int c = 0; c < kDH; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(src + lane_off + c, v);
-        tmem_ld_wait();
-        if (kv < N) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+        for (int k = 0; k < 2; ++k) {
+          u32x8 o;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            d4[k] = make_uint4(pack_bf16(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
-                               pack_bf16(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
-                               pack_bf16(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
-                               pack_bf16(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
+          for (int j = 0; j < 8; ++j)
+            o.v[j] = pack_bf16(__uint_as_float(v[16 * k + 2 * j]), __uint_as_float(v[16 * k + 2 * j + 1]));
+          st_global_256(dst + c + 16 * k, o);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 static int make_tok_tmap(CUtensorMap* m, const void* base, int B, int N, int row_elems) {
@@ -515,7 +528,9 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
 extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                                 float* dq_accum, float* delta, int32_t B, int32_t N, int32_t H, float scale,
                                 float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site, void* stream) {
-  VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && dq_accum && delta, "vs_attention_bwd: null pointer");
+  VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && dq_accum, "vs_attention_bwd: null pointer");
+  VS_CHECK_ARG(((uintptr_t)ctx % 32 == 0) && ((uintptr_t)dctx % 32 == 0) && ((uintptr_t)dqkv % 32 == 0),
+               "vs_attention_bwd: ctx / dctx / dqkv must be 32-byte aligned");
   VS_CHECK_ARG(B > 0 && N > 0 && H > 0, "vs_attention_bwd: bad shape");
   VS_CHECK_ARG(B <= 65535 && H <= 65535, "vs_attention_bwd: B/H exceed grid limits");
   VS_CHECK_ARG(sm_count() > 0, "vs_attention_bwd: no CUDA device");
@@ -532,16 +547,14 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
                                        AttnBwdSmem::kTotal));
     attr = true;
   }
-  const long long rows = (long long)B * N * H;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx,
-                                                                delta, B, N, H);
-  VS_CHECK_LAUNCH();
   VS_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * N * D * sizeof(float), st));
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * N)) return rc2;
+  (void)delta;  // kept in the ABI for callers that pre-allocated it; delta is computed inside the kernel
   dim3 grid((N + kBKV - 1) / kBKV, H, B);
-  attn_bwd_kernel<<<grid, 160, AttnBwdSmem::kTotal, st>>>(tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, dq_accum, B, N, H,
-                                                          scale, dc);
+  attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tq, tdo, (const __nv_bfloat16*)ctx,
+                                                                  (const __nv_bfloat16*)dctx, lse,
+                                                                  (__nv_bfloat16*)dqkv, dq_accum, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
