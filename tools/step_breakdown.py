@@ -93,3 +93,40 @@ tot = sum(v[2] for v in agg.values())
 print(f"GEMM total {tot:.2f} ms over {len(ev)} launches")
 for tag, (n, fl, ms) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
     print(f"  {ms:7.3f} ms n={n:3d} avg {ms/n*1e3:7.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  {tag}")
+
+# ---- every libvitseg wrapper timed with CUDA events (one eager step)
+K.gemm = orig
+E.K.gemm = orig
+import visiontransformer_b200.losses as LS  # noqa: E402
+names = [n for n in dir(K) if callable(getattr(K, n)) and not n.startswith("_") and n not in
+         ("check", "ptr", "stream", "require_cuda", "enable_gemm_timing", "collect_gemm_timing", "launch_count",
+          "reset_launch_count", "GemmDesc")]
+records = []
+origs = {}
+
+
+def wrap(name, fn):
+    def inner(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        records.append((name, e0, e1))
+        return r
+    return inner
+
+
+for n in names:
+    origs[n] = getattr(K, n)
+    setattr(K, n, wrap(n, origs[n]))
+step(0)
+torch.cuda.synchronize()
+agg2 = collections.OrderedDict()
+for n, e0, e1 in records:
+    a = agg2.setdefault(n, [0, 0.0])
+    a[0] += 1
+    a[1] += e0.elapsed_time(e1)
+tot2 = sum(v[1] for v in agg2.values())
+print(f"all libvitseg calls: {tot2:.2f} ms")
+for n, (c, ms) in sorted(agg2.items(), key=lambda kv: -kv[1][1]):
+    print(f"  {ms:7.3f} ms n={c:3d} avg {ms/c*1e3:7.1f} us  {n}")

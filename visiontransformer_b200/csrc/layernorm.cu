@@ -55,8 +55,11 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // dx_out = dx_in + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  dgamma += sum dy*xhat; dbeta += sum dy
+// Occupancy matters more than anything else here: the kernel is a chain of dependent global loads, two warp
+// reductions and stores per row.  gamma lives in shared memory (not 4*NV registers) and the register budget is capped
+// so that two 8-warp blocks fit per SM (first version: 254 registers, one block per SM, ~2 TB/s).
 template <int NV, bool DY_F32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dx_in, int M,
               float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
@@ -64,15 +67,15 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
   constexpr int D = NV * 128;
   __shared__ float s_dg[D];
   __shared__ float s_db[D];
-  for (int i = threadIdx.x; i < D; i += blockDim.x) { s_dg[i] = 0.0f; s_db[i] = 0.0f; }
+  __shared__ __align__(16) float s_gamma[D];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { s_dg[i] = 0.0f; s_db[i] = 0.0f; s_gamma[i] = gamma[i]; }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  float4 g[NV];
+  const float4* g = reinterpret_cast<const float4*>(s_gamma) + lane;   // g[32 * i]
   float4 acc_g[NV], acc_b[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     acc_g[i] = make_float4(0, 0, 0, 0);
     acc_b[i] = make_float4(0, 0, 0, 0);
   }
@@ -92,7 +95,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
       }
       const float4 xv = reinterpret_cast<const float4*>(x + (size_t)row * D)[lane + 32 * i];
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      const float gx = dy[i].x * g[i].x, gy = dy[i].y * g[i].y, gz = dy[i].z * g[i].z, gw = dy[i].w * g[i].w;
+      const float4 gm = g[32 * i];
+      const float gx = dy[i].x * gm.x, gy = dy[i].y * gm.y, gz = dy[i].z * gm.z, gw = dy[i].w * gm.w;
       s1 += (gx + gy) + (gz + gw);
       s2 += (gx * xh[i].x + gy * xh[i].y) + (gz * xh[i].z + gw * xh[i].w);
       acc_g[i].x += dy[i].x * xh[i].x; acc_g[i].y += dy[i].y * xh[i].y;
@@ -103,11 +107,12 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
     const float m2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
+      const float4 gm = g[32 * i];
       float4 o;
-      o.x = rs * (dy[i].x * g[i].x - m1 - xh[i].x * m2);
-      o.y = rs * (dy[i].y * g[i].y - m1 - xh[i].y * m2);
-      o.z = rs * (dy[i].z * g[i].z - m1 - xh[i].z * m2);
-      o.w = rs * (dy[i].w * g[i].w - m1 - xh[i].w * m2);
+      o.x = rs * (dy[i].x * gm.x - m1 - xh[i].x * m2);
+      o.y = rs * (dy[i].y * gm.y - m1 - xh[i].y * m2);
+      o.z = rs * (dy[i].z * gm.z - m1 - xh[i].z * m2);
+      o.w = rs * (dy[i].w * gm.w - m1 - xh[i].w * m2);
       if (dx_in) {
         const float4 r = reinterpret_cast<const float4*>(dx_in + (size_t)row * D)[lane + 32 * i];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -174,7 +179,7 @@ extern "C" int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* 
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_layernorm_bwd: no CUDA device");
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = nsm * 4;
+  int grid = nsm * 2;   // two resident blocks per SM, each a persistent loop over rows
   if (grid > (M + 7) / 8) grid = (M + 7) / 8;
   __nv_bfloat16* db = (__nv_bfloat16*)dx_bf16;
   DropCfg dc{0u, 1.0f, nullptr, 0u};
