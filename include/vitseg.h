@@ -209,12 +209,13 @@ int vs_paed_multiclass_dense(const float* msk, const float* prob, float* t1, flo
 /* ------------------------------------------------------------------------------------------------
  * Dropout glue.  vs_dropout_rows: in-place dropout of an fp32 buffer of n elements (n % 4 == 0) + optional bf16 copy —
  * the embedding dropout (TF:126) in forward and the same mask on the gradient in backward.  vs_dropout_mask writes
- * the keep mask of a site as bytes (scheme 0: hidden-state pair hash, scheme 1: attention per-element hash); tests.
+ * the keep mask of a site as bytes (scheme 0: hidden states, dense index space; scheme 1: attention probabilities
+ * viewed as rows of row_len keys); tests.
  * ------------------------------------------------------------------------------------------------ */
 int vs_dropout_rows(float* x, void* x_bf16, int64_t n, float dropout_p, const uint32_t* dropout_seed,
                     uint32_t dropout_site, void* stream);
-int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, float dropout_p, const uint32_t* dropout_seed,
-                    uint32_t dropout_site, void* stream);
+int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, int32_t row_len, float dropout_p,
+                    const uint32_t* dropout_seed, uint32_t dropout_site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight shadows: fp32 master -> bf16 copy (one pass), plus utility conversions.

@@ -23,8 +23,10 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
 
 
-def _mask(K, n, scheme, drop):
-    return K.dropout_mask(torch.empty(n, device=drop[1].device, dtype=torch.uint8), scheme, drop).float()
+def _mask(K, n, scheme, drop, row_len=0):
+    if scheme == 1 and row_len == 0:
+        row_len = 256
+    return K.dropout_mask(torch.empty(n, device=drop[1].device, dtype=torch.uint8), scheme, drop, row_len).float()
 
 
 def test_mask_statistics_and_determinism():
@@ -99,7 +101,7 @@ def test_attention_dropout_forward_backward(B, N, H):
     ctx = torch.empty(B, N, H, 64, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, H, N, device=dev)
     K.attention_fwd(qkv, ctx, lse, B, N, H, 0.125, dropout=drop)
-    mask = _mask(K, B * H * N * N, 1, drop).view(B, H, N, N)
+    mask = _mask(K, B * H * N * N, 1, drop, N).view(B, H, N, N)
     scale = 1.0 / (1.0 - round(p * 65536) / 65536.0)
     q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).float().requires_grad_(True) for i in range(3)]
     s = (q @ k.transpose(-1, -2)) * 0.125
@@ -210,7 +212,7 @@ def test_training_step_with_dropout_matches_masked_reference():
     for site in (0, 1, 2, 3, 4):
         masks[site] = _mask(K, B * N * D, 0, (ph, eng.rng_step, site)).cpu()
     for i in range(2):
-        masks[1000 + i] = _mask(K, B * H * N * N, 1, (pa, eng.rng_step, 1000 + i)).cpu()
+        masks[1000 + i] = _mask(K, B * H * N * N, 1, (pa, eng.rng_step, 1000 + i), N).cpu()
     sc = lambda p: 1.0 / (1.0 - round(p * 65536) / 65536.0)  # noqa: E731
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     ref = _masked_reference_loss(leaves, x, y, cfg, masks, sc(ph), sc(pa))

@@ -47,7 +47,7 @@ _SIGS = {
     "vs_attention_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                          c_float, c_float, c_void_p, C.c_uint32, c_void_p],
     "vs_dropout_rows": [c_void_p, c_void_p, c_i64, c_float, c_void_p, C.c_uint32, c_void_p],
-    "vs_dropout_mask": [c_void_p, c_i64, c_int, c_float, c_void_p, C.c_uint32, c_void_p],
+    "vs_dropout_mask": [c_void_p, c_i64, c_int, c_int, c_float, c_void_p, C.c_uint32, c_void_p],
     "vs_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_cls_rows": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -26,6 +26,12 @@ constexpr int kBKV = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // write 32 consecutive bf16 (columns c32*32 .. +32 of row r) of a [128 x 128] bf16 tile stored as two
 // [128 rows x 128 B] 128B-swizzled halves
 __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c32, const float (&f)[32]) {
@@ -152,7 +158,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     uint8_t* sP = smem + AttnFwdSmem::kP;
     const float sl2 = scale * kLog2e;
     const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
-    const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)N;
+    const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);  // pair index base
     float m_run = -INFINITY, l_run = 0.0f;
     float o_acc[kDH];
 #pragma unroll
@@ -176,7 +182,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
           if (c + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
       }
       const float m_new = fmaxf(m_run, m_blk * sl2);
-      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block (m_run = -inf)
       float l_blk = 0.0f;
       // pass 2: probabilities -> bf16 smem (A operand of P·V)
       for (int c = 0; c < ncols; c += 32) {
@@ -186,11 +192,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float pv = (c + i < nvalid) ? exp2f(__uint_as_float(v[i]) * sl2 - m_new) : 0.0f;
+          const float pv = (c + i < nvalid) ? ex2_approx(__uint_as_float(v[i]) * sl2 - m_new) : 0.0f;
           l_blk += pv;   // the softmax normaliser uses the un-dropped probabilities (dropout acts on softmax output)
           f[i] = pv;
-          if (drop.thresh != 0u)
-            f[i] = drop_keep(drow + (uint32_t)(kv0 + c + i), dseed, drop.thresh) ? pv * drop.scale : 0.0f;
+        }
+        if (drop.thresh != 0u) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {   // keys 2k, 2k+1 of a query row share one hash
+            bool k0, k1;
+            drop_keep2(2u * (drow + (uint32_t)((kv0 + c + i) >> 1)), dseed, drop.thresh, k0, k1);
+            f[i] = k0 ? f[i] * drop.scale : 0.0f;
+            f[i + 1] = k1 ? f[i + 1] * drop.scale : 0.0f;
+          }
         }
         store_row32_sw128(sP, r, c >> 5, f);
       }
@@ -377,7 +390,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const uint32_t ph = i & 1;
       const int q = i * kBQ + r;
       const bool q_ok = q < N;
-      const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)N;
+      const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);
       float lse2 = 0.0f, dlt = 0.0f;
       if (q_ok) {
         lse2 = lse[((size_t)b * H + h) * N + q] * kLog2e;
@@ -407,18 +420,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           tmem_ld32(tm_dp + lane_off + c, dv);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const bool ok = q_ok && (c + k < nvalid_kv);
-            const float pv = ok ? exp2f(__uint_as_float(sv[k]) * sl2 - lse2) : 0.0f;
-            float pd = pv, dpv = __uint_as_float(dv[k]);
-            if (drop.thresh != 0u) {
-              // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
-              const bool keep = drop_keep(drow + (uint32_t)(kv0 + c + k), dseed, drop.thresh);
-              pd = keep ? pv * drop.scale : 0.0f;
-              dpv = keep ? dpv * drop.scale : 0.0f;
+          for (int k = 0; k < 32; k += 2) {
+            bool keep[2] = {true, true};
+            if (drop.thresh != 0u)
+              drop_keep2(2u * (drow + (uint32_t)((kv0 + c + k) >> 1)), dseed, drop.thresh, keep[0], keep[1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const bool ok = q_ok && (c + k + u < nvalid_kv);
+              const float pv = ok ? ex2_approx(__uint_as_float(sv[k + u]) * sl2 - lse2) : 0.0f;
+              float pd = pv, dpv = __uint_as_float(dv[k + u]);
+              if (drop.thresh != 0u) {
+                // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
+                pd = keep[u] ? pv * drop.scale : 0.0f;
+                dpv = keep[u] ? dpv * drop.scale : 0.0f;
+              }
+              pf[k + u] = pd;
+              dsf[k + u] = pv * (dpv - dlt) * scale;
             }
-            pf[k] = pd;
-            dsf[k] = pv * (dpv - dlt) * scale;
           }
         } else {
 #pragma unroll
@@ -517,7 +535,7 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
     attr = true;
   }
   DropCfg dc;
-  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * N)) return rc2;
+  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
   attn_fwd_kernel<<<grid, 160, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, (__nv_bfloat16*)ctx, lse, B, N, H,
                                                                            scale, dc);
@@ -549,7 +567,7 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   }
   VS_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * N * D * sizeof(float), st));
   DropCfg dc;
-  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * N)) return rc2;
+  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
   (void)delta;  // kept in the ABI for callers that pre-allocated it; delta is computed inside the kernel
   dim3 grid((N + kBKV - 1) / kBKV, H, B);
   attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tq, tdo, (const __nv_bfloat16*)ctx,

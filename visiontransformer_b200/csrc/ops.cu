@@ -333,8 +333,9 @@ __global__ void dropout_rows_kernel(float* __restrict__ x, __nv_bfloat16* __rest
 }
 
 // writes the keep mask (1/0 bytes) of a dropout site: scheme 0 = pair hash over a dense [n] index space (hidden
-// states), scheme 1 = per-element hash (attention probabilities).  Test / debugging aid.
-__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, long long n, int scheme, const DropCfg drop) {
+// states), scheme 1 = attention probabilities viewed as [n / row_len, row_len].  Test / debugging aid.
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, long long n, int scheme, int row_len,
+                                    const DropCfg drop) {
   const uint32_t sd = drop_seed(drop);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     bool keep;
@@ -343,7 +344,12 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ out, long long n, int 
       drop_keep2((uint32_t)(i & ~1LL), sd, drop.thresh, k0, k1);
       keep = (i & 1) ? k1 : k0;
     } else {
-      keep = drop_keep((uint32_t)i, sd, drop.thresh);
+      // attention probabilities [rows, row_len]: keys 2k, 2k+1 of a row share hash(row * ceil(row_len/2) + k)
+      const long long row = i / row_len;
+      const int kv = int(i - row * row_len);
+      bool k0, k1;
+      drop_keep2(2u * ((uint32_t)row * (uint32_t)((row_len + 1) >> 1) + (uint32_t)(kv >> 1)), sd, drop.thresh, k0, k1);
+      keep = (kv & 1) ? k1 : k0;
     }
     out[i] = keep ? 1 : 0;
   }
@@ -527,14 +533,15 @@ extern "C" int vs_dropout_rows(float* x, void* x_bf16, int64_t n, float dropout_
   return 0;
 }
 
-extern "C" int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, float dropout_p, const uint32_t* dropout_seed,
-                               uint32_t dropout_site, void* stream) {
-  VS_CHECK_ARG(out && n > 0 && n < (1LL << 32) && (scheme == 0 || scheme == 1), "vs_dropout_mask: bad arguments");
+extern "C" int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, int32_t row_len, float dropout_p,
+                               const uint32_t* dropout_seed, uint32_t dropout_site, void* stream) {
+  VS_CHECK_ARG(out && n > 0 && n < (1LL << 32) && (scheme == 0 || (scheme == 1 && row_len > 0 && n % row_len == 0)),
+               "vs_dropout_mask: bad arguments");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_dropout_mask: no CUDA device");
   DropCfg dc;
   if (int rc = make_drop_cfg(&dc, dropout_p, dropout_seed, dropout_site, "vs_dropout_mask")) return rc;
-  dropout_mask_kernel<<<grid_for(n, 256, nsm), 256, 0, (cudaStream_t)stream>>>(out, n, scheme, dc);
+  dropout_mask_kernel<<<grid_for(n, 256, nsm), 256, 0, (cudaStream_t)stream>>>(out, n, scheme, row_len, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }

@@ -169,9 +169,10 @@ def dropout_rows(x, x_bf16, dropout):
     check(_lib.load().vs_dropout_rows(ptr(x), ptr(x_bf16), x.numel(), *_drop(dropout), stream()), "vs_dropout_rows")
 
 
-def dropout_mask(out, scheme, dropout):
+def dropout_mask(out, scheme, dropout, row_len=0):
     assert out.dtype == torch.uint8 and out.is_contiguous()
-    check(_lib.load().vs_dropout_mask(ptr(out), out.numel(), scheme, *_drop(dropout), stream()), "vs_dropout_mask")
+    check(_lib.load().vs_dropout_mask(ptr(out), out.numel(), scheme, row_len, *_drop(dropout), stream()),
+          "vs_dropout_mask")
     return out
 
 
