@@ -246,28 +246,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 // ================================================================================================
 // backward
 // ================================================================================================
+// ------------------------------------------------------------------------------------------------
+// Backward.  One CTA per (64-key block, head, batch); two CTAs are resident per SM (80 KB smem, 256 TMEM columns
+// each) so that one CTA's exp / dS phase overlaps the other's TMA and MMA phases — with 128-key blocks (448 TMEM
+// columns, 128 KB smem) only one CTA fitted and every phase of it was exposed (r01: 146-212 us per layer).
+//   TMEM: S [128 q x 64 k] cols 0-63 | dP 64-127 | dV [64 k x 64 d] 128-191 | dK 192-255 ; dQ_i [128 q x 64 d] reuses
+//   the S columns once the compute warps have consumed S and dP.  dV / dK are M = 64 accumulators: key row m lives in
+//   TMEM lane (m % 16) + 32 * (m / 16).
+// 8 compute warps: warp w owns TMEM lane quadrant (w & 3) and key columns [32 * (w >> 2), +32) of the S / dP tiles.
+// delta_i = sum_d dO_i,d O_i,d is computed in-kernel from the bf16 rows of O and dO.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKB = 64;          // keys per CTA
 struct AttnBwdSmem {
-  static constexpr int kK = 0;
-  static constexpr int kV = 16384;
-  static constexpr int kQ = 32768;
-  static constexpr int kDO = 49152;
-  static constexpr int kP = 65536;             // 32 KB
-  static constexpr int kDS = 65536 + 32768;    // 32 KB
-  static constexpr int kBar = 65536 + 65536;
+  static constexpr int kK = 0;                 // 64 x 128 B
+  static constexpr int kV = 8192;
+  static constexpr int kQ = 16384;             // 128 x 128 B
+  static constexpr int kDO = 32768;
+  static constexpr int kP = 49152;             // 128 x 128 B (64 keys)
+  static constexpr int kDS = 65536;
+  static constexpr int kBar = 81920;
   static constexpr int kTotal = kBar + 128 + 1024;
 };
-
-// 8 compute warps: warp w owns TMEM lane quadrant (w & 3) and key-column half (w >> 2) of the 128x128 S / dP tiles,
-// so the exp / dS phase (the serialised part of the CTA) takes half as long as with one thread per query row.
-// delta_i = sum_d dO_i,d O_i,d is computed in the kernel (each thread reads its query row of O and dO straight from
-// global while the MMAs run) — no separate pre-pass over ctx / dctx.
 constexpr int kBwdThreads = 288;
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
-                const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_accum, int B,
-                int N, int H, float scale, const DropCfg drop) {
+__global__ void __launch_bounds__(kBwdThreads, 2)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_constant__ CUtensorMap tmap_q,
+                const __grid_constant__ CUtensorMap tmap_do, const __nv_bfloat16* __restrict__ ctx,
+                const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
+                __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_accum, int B, int N, int H, float scale,
+                const DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBar);
@@ -276,35 +283,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* bar_s = bars + 2;
   uint64_t* bar_pds = bars + 3;
   uint64_t* bar_dq = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_dqr = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * kBKV, h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = blockIdx.x * kKB, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kDH;
   const int nq = (N + kBQ - 1) / kBQ;
-  const int nvalid_kv = min(kBKV, N - kv0);
+  const int nvalid_kv = min(kKB, N - kv0);
   const int ncols = (nvalid_kv + 15) & ~15;
 
   if (warp == 8) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmap_qkv);
+      tma_prefetch_desc(&tmap_kv);
+      tma_prefetch_desc(&tmap_q);
       tma_prefetch_desc(&tmap_do);
       mbar_init(bar_kv, 1);
       mbar_init(bar_q, 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_pds, 256);
       mbar_init(bar_dq, 1);
+      mbar_init(bar_dqr, 256);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, 256);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
-                 tm_dq = tmem_base + 384;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 64, tm_dv = tmem_base + 128, tm_dk = tmem_base + 192,
+                 tm_dq = tmem_base;
 
   if (warp == 8) {
     // ---------------------------------------------------------------- control warp (converged; elected lane issues)
@@ -315,11 +325,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const uint32_t aP = smem_u32(smem + AttnBwdSmem::kP);
     const uint32_t aDS = smem_u32(smem + AttnBwdSmem::kDS);
     if (elect_one()) {
-      mbar_expect_tx(bar_kv, 2 * 16384);
-      tma_load_3d(sK, &tmap_qkv, bar_kv, D + h * kDH, kv0, b);
-      tma_load_3d(sV, &tmap_qkv, bar_kv, 2 * D + h * kDH, kv0, b);
+      mbar_expect_tx(bar_kv, 2 * 8192);
+      tma_load_3d(sK, &tmap_kv, bar_kv, D + h * kDH, kv0, b);
+      tma_load_3d(sV, &tmap_kv, bar_kv, 2 * D + h * kDH, kv0, b);
       mbar_expect_tx(bar_q, 2 * 16384);
-      tma_load_3d(sQ, &tmap_qkv, bar_q, h * kDH, 0, b);
+      tma_load_3d(sQ, &tmap_q, bar_q, h * kDH, 0, b);
       tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, 0, b);
     }
     __syncwarp();
@@ -327,9 +337,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     for (int i = 0; i < nq; ++i) {
       const uint32_t ph = i & 1;
       mbar_wait(bar_q, ph);
+      if (i > 0) mbar_wait(bar_dqr, ph ^ 1);   // dQ_{i-1} (aliasing the S columns) has been read out
       tc_fence_after();
       if (elect_one()) {
-        // S = Q K^T and dP = dO V^T, both [128 q x ncols kv], reduction over head_dim
+        // S = Q K^T and dP = dO V^T, both [128 q x ncols k], reduction over head_dim
         const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
         const uint64_t qd = umma_desc_sw128(smem_u32(sQ), 16, 1024);
         const uint64_t kd = umma_desc_sw128(smem_u32(sK), 16, 1024);
@@ -345,8 +356,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_wait(bar_pds, ph);
       tc_fence_after();
       if (elect_one()) {
-        // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 128 keys, K = 128 queries)
-        const uint32_t idesc = umma_idesc_bf16(kBKV, kDH, 1, 1);
+        // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 64 keys, K = 128 queries), B MN-major (N = 64)
+        const uint32_t idesc = umma_idesc_bf16(kKB, kDH, 1, 1);
 #pragma unroll
         for (int kk = 0; kk < kBQ / 16; ++kk) {
           const uint64_t pd = umma_desc_sw128(aP + kk * 2048, 16384, 1024);
@@ -362,7 +373,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         // dQ_i = dS K : A = dS K-major (M = 128 queries, K = ncols keys), B = K MN-major (N = 64, K = keys)
         const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
         for (int kk = 0; kk < ncols / 16; ++kk) {
-          const uint64_t dsd = umma_desc_sw128(aDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t dsd = umma_desc_sw128(aDS + kk * 32, 16, 1024);
           const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
           umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
         }
@@ -372,7 +383,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_wait(bar_dq, ph);
       if (i + 1 < nq && elect_one()) {
         mbar_expect_tx(bar_q, 2 * 16384);
-        tma_load_3d(sQ, &tmap_qkv, bar_q, h * kDH, (i + 1) * kBQ, b);
+        tma_load_3d(sQ, &tmap_q, bar_q, h * kDH, (i + 1) * kBQ, b);
         tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, (i + 1) * kBQ, b);
       }
       __syncwarp();
@@ -412,18 +423,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 64 + cc * 32;
-        float pf[32], dsf[32];
+        const int c = half * 32 + cc * 16;          // key column of this 16-wide chunk
+        uint32_t pk[8], dsk[8];
         if (c < ncols) {
-          uint32_t sv[32], dv[32];
-          tmem_ld32(tm_s + lane_off + c, sv);
-          tmem_ld32(tm_dp + lane_off + c, dv);
+          uint32_t sv[16], dv[16];
+          tmem_ld16(tm_s + lane_off + c, sv);
+          tmem_ld16(tm_dp + lane_off + c, dv);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; k += 2) {
+          for (int k = 0; k < 16; k += 2) {
             bool keep[2] = {true, true};
             if (drop.thresh != 0u)
               drop_keep2(2u * (drow + (uint32_t)((kv0 + c + k) >> 1)), dseed, drop.thresh, keep[0], keep[1]);
+            float pdv[2], dsv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const bool ok = q_ok && (c + k + u < nvalid_kv);
@@ -434,31 +446,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 pd = keep[u] ? pv * drop.scale : 0.0f;
                 dpv = keep[u] ? dpv * drop.scale : 0.0f;
               }
-              pf[k + u] = pd;
-              dsf[k + u] = pv * (dpv - dlt) * scale;
+              pdv[u] = pd;
+              dsv[u] = pv * (dpv - dlt) * scale;
             }
+            pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
+            dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) { pf[k] = 0.0f; dsf[k] = 0.0f; }
+          for (int k = 0; k < 8; ++k) { pk[k] = 0u; dsk[k] = 0u; }
         }
-        store_row32_sw128(sP, r, c >> 5, pf);
-        store_row32_sw128(sDS, r, c >> 5, dsf);
+        const uint32_t slot = uint32_t(c >> 3);     // 16-byte slot inside the 128-byte (64-key) row
+        *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot)) = make_uint4(dsk[0], dsk[1], dsk[2], dsk[3]);
+        *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot + 1)) = make_uint4(dsk[4], dsk[5], dsk[6], dsk[7]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_pds);
       mbar_wait(bar_dq, ph);
       tc_fence_after();
-      {
-        // dQ partial of this key block: this thread owns head dims [32*half, +32) of query row q
-        uint32_t v[32];
-        tmem_ld32(tm_dq + lane_off + half * 32, v);
+      // dQ partial of this key block: this thread owns head dims [32*half, +32) of query row q
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(tm_dq + lane_off + half * 32 + cc * 16, v);
         tmem_ld_wait();
         if (q_ok) {
-          float* dst = dq_accum + ((size_t)b * N + q) * D + h * kDH + half * 32;
+          float* dst = dq_accum + ((size_t)b * N + q) * D + h * kDH + half * 32 + cc * 16;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
+          for (int k = 0; k < 4; ++k)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k),
                          "f"(__uint_as_float(v[4 * k])), "f"(__uint_as_float(v[4 * k + 1])),
                          "f"(__uint_as_float(v[4 * k + 2])), "f"(__uint_as_float(v[4 * k + 3]))
@@ -466,37 +484,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
       }
       tc_fence_before();
+      mbar_arrive(bar_dqr);
     }
-    // dK (warps 0-3) and dV (warps 4-7): row r <-> key kv0 + r.  All MMAs completed with the last bar_dq phase.
-    const int kv = kv0 + r;
+    // dK (warps 0-3) and dV (warps 4-7), M = 64 accumulator layout: lanes 0-15 of quadrant `quad` hold keys
+    // 16*quad .. 16*quad+15.  All MMAs completed with the last bar_dq phase.
+    const int kv = kv0 + quad * 16 + lane;
+    const bool kv_ok = lane < 16 && kv < N;
     const uint32_t src = half == 0 ? tm_dk : tm_dv;
     __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (half == 0 ? D : 2 * D) + h * kDH;
 #pragma unroll
-    for (int c = 0; c < kDH; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(src + lane_off + c, v);
+    for (int c = 0; c < kDH; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(src + lane_off + c, v);
       tmem_ld_wait();
-      if (kv < N) {
+      if (kv_ok) {
+        u32x8 o;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          u32x8 o;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o.v[j] = pack_bf16(__uint_as_float(v[16 * k + 2 * j]), __uint_as_float(v[16 * k + 2 * j + 1]));
-          st_global_256(dst + c + 16 * k, o);
-        }
+        for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        st_global_256(dst + c, o);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
 
-static int make_tok_tmap(CUtensorMap* m, const void* base, int B, int N, int row_elems) {
+static int make_tok_tmap(CUtensorMap* m, const void* base, int B, int N, int row_elems, int box_rows = 128) {
   uint64_t dims[3] = {(uint64_t)row_elems, (uint64_t)N, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)row_elems * 2, (uint64_t)N * row_elems * 2};
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return make_tmap_bf16(m, base, 3, dims, strides, box);
 }
 
@@ -554,8 +571,10 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   VS_CHECK_ARG(sm_count() > 0, "vs_attention_bwd: no CUDA device");
   cudaStream_t st = (cudaStream_t)stream;
   const int D = H * kDH;
-  CUtensorMap tq, tdo;
-  int rc = make_tok_tmap(&tq, qkv, B, N, 3 * D);
+  CUtensorMap tkv, tq, tdo;
+  int rc = make_tok_tmap(&tkv, qkv, B, N, 3 * D, kKB);
+  if (rc) return rc;
+  rc = make_tok_tmap(&tq, qkv, B, N, 3 * D);
   if (rc) return rc;
   rc = make_tok_tmap(&tdo, dctx, B, N, D);
   if (rc) return rc;
@@ -569,8 +588,8 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
   (void)delta;  // kept in the ABI for callers that pre-allocated it; delta is computed inside the kernel
-  dim3 grid((N + kBKV - 1) / kBKV, H, B);
-  attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tq, tdo, (const __nv_bfloat16*)ctx,
+  dim3 grid((N + kKB - 1) / kKB, H, B);
+  attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tkv, tq, tdo, (const __nv_bfloat16*)ctx,
                                                                   (const __nv_bfloat16*)dctx, lse,
                                                                   (__nv_bfloat16*)dqkv, dq_accum, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();

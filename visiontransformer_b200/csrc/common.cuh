@@ -101,27 +101,30 @@ __device__ __forceinline__ u32x8 ld_global_nc_256(const void* ptr) {
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level): 2 MUFU ops (rcp, ex2) + ~8 FMAs per
 // element instead of erff()'s ~30-instruction branchy path, which made the fc1 / fc2-dgrad GEMM epilogues slower
 // than their MMA main loops.  The tail 0.5*(1+erf) is formed without cancellation: Phi(x<0) = 0.5*poly*e.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
+// half_tail(|x|) = 0.5 * erfc(|x| / sqrt(2)) = Phi(-|x|), and e = exp(-x^2/2).  Constants are pre-folded
+// (p/sqrt(2) into the rcp argument, 0.5 into the polynomial, -0.5*log2(e) into the exponent): 11 instructions.
+__device__ __forceinline__ float gelu_half_tail(float ax, float x, float& e) {
   float t, ex;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.4426950408889634f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_tail = 0.5f * p * t * ex;  // 0.5 * erfc(z)
-  cdf = x >= 0.0f ? 1.0f - half_tail : half_tail;
-  e = ex;  // exp(-x^2/2)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164190f, ax, 1.0f)));          // 0.3275911 / sqrt(2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"((x * x) * -0.72134752044448170368f));  // -0.5 * log2(e)
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);   // 0.5 * {1.061405429, -1.453152027, 1.421413741, ...}
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  e = ex;
+  return (p * t) * ex;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
+  // x * Phi(x) = max(x, 0) - |x| * Phi(-|x|): no select, no cancellation in the tail
+  float e;
+  const float ax = fabsf(x);
+  const float h = gelu_half_tail(ax, x, e);
+  return fmaf(-ax, h, fmaxf(x, 0.0f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
+  float e;
+  const float h = gelu_half_tail(fabsf(x), x, e);
+  const float cdf = x >= 0.0f ? 1.0f - h : h;
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
