@@ -254,8 +254,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 //   the S columns once the compute warps have consumed S and dP.  dV / dK are M = 64 accumulators: key row m lives in
 //   TMEM lane (m % 16) + 32 * (m / 16).
 // 8 compute warps: warp w owns TMEM lane quadrant (w & 3) and key columns [32 * (w >> 2), +32) of the S / dP tiles.
-// delta_i = sum_d dO_i,d O_i,d is computed in-kernel from the bf16 rows of O and dO.
+// delta_i = sum_d dO_i,d O_i,d comes from attn_delta_kernel.
 // ------------------------------------------------------------------------------------------------
+// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]: one thread per 64-element row, 256-bit loads.  Computed once per
+// layer: doing it inside the backward CTAs (8x redundantly) was 52 % of that kernel's instructions (ncu r01).
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                  float* __restrict__ delta, int B, int N, int H) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (long long)B * N * H) return;
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const u32x8 ov = ld_global_nc_256(o + row * kDH + 16 * k);
+    const u32x8 gv = ld_global_nc_256(dout + row * kDH + 16 * k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // bf16 -> fp32 is a 16-bit shift: low half via shl, high half via mask
+      const float a0 = __uint_as_float(ov.v[j] << 16), a1 = __uint_as_float(ov.v[j] & 0xFFFF0000u);
+      const float g0 = __uint_as_float(gv.v[j] << 16), g1 = __uint_as_float(gv.v[j] & 0xFFFF0000u);
+      acc = fmaf(a0, g0, acc);
+      acc = fmaf(a1, g1, acc);
+    }
+  }
+  const int hh = int(row % H);
+  const long long bn = row / H;
+  const int n = int(bn % N);
+  const int bb = int(bn / N);
+  delta[((size_t)bb * H + hh) * N + n] = acc;
+}
+
 constexpr int kKB = 64;          // keys per CTA
 struct AttnBwdSmem {
   static constexpr int kK = 0;                 // 64 x 128 B
@@ -271,10 +299,9 @@ constexpr int kBwdThreads = 288;
 
 __global__ void __launch_bounds__(kBwdThreads, 2)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_constant__ CUtensorMap tmap_q,
-                const __grid_constant__ CUtensorMap tmap_do, const __nv_bfloat16* __restrict__ ctx,
-                const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
-                __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_accum, int B, int N, int H, float scale,
-                const DropCfg drop) {
+                const __grid_constant__ CUtensorMap tmap_do, const float* __restrict__ lse,
+                const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_accum,
+                int B, int N, int H, float scale, const DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBar);
@@ -397,27 +424,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
     uint8_t* sDS = smem + AttnBwdSmem::kDS;
     const float sl2 = scale * kLog2e;
     const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
+    const bool tail_block = nvalid_kv < kKB;
     for (int i = 0; i < nq; ++i) {
       const uint32_t ph = i & 1;
       const int q = i * kBQ + r;
       const bool q_ok = q < N;
       const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);
-      float lse2 = 0.0f, dlt = 0.0f;
+      // rows beyond the sequence get lse = +inf so that exp2(s - lse) = 0 without a select
+      float lse2 = INFINITY, dlt = 0.0f;
       if (q_ok) {
         lse2 = lse[((size_t)b * H + h) * N + q] * kLog2e;
-        // delta = rowsum(dO * O) over the 64 head dims, in fp32 from the bf16 rows
-        const size_t off = ((size_t)b * N + q) * D + h * kDH;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const u32x8 ov = ld_global_nc_256(ctx + off + 16 * k);
-          const u32x8 gv = ld_global_nc_256(dctx + off + 16 * k);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 a = unpack_bf16(ov.v[j]), g = unpack_bf16(gv.v[j]);
-            dlt = fmaf(a.x, g.x, dlt);
-            dlt = fmaf(a.y, g.y, dlt);
-          }
-        }
+        dlt = delta[((size_t)b * H + h) * N + q];
       }
       mbar_wait(bar_s, ph);
       tc_fence_after();
@@ -438,16 +456,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
             float pdv[2], dsv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const bool ok = q_ok && (c + k + u < nvalid_kv);
-              const float pv = ok ? ex2_approx(__uint_as_float(sv[k + u]) * sl2 - lse2) : 0.0f;
-              float pd = pv, dpv = __uint_as_float(dv[k + u]);
-              if (drop.thresh != 0u) {
-                // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
-                pd = keep[u] ? pv * drop.scale : 0.0f;
-                dpv = keep[u] ? dpv * drop.scale : 0.0f;
-              }
-              pdv[u] = pd;
-              dsv[u] = pv * (dpv - dlt) * scale;
+              float pv = ex2_approx(__uint_as_float(sv[k + u]) * sl2 - lse2);
+              if (tail_block) pv = (c + k + u < nvalid_kv) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
+              // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
+              const float mk = keep[u] ? dscale : 0.0f;
+              pdv[u] = pv * mk;
+              dsv[u] = (pv * scale) * (__uint_as_float(dv[k + u]) * mk - dlt);
             }
             pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
             dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
@@ -563,7 +577,7 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
 extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                                 float* dq_accum, float* delta, int32_t B, int32_t N, int32_t H, float scale,
                                 float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site, void* stream) {
-  VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && dq_accum, "vs_attention_bwd: null pointer");
+  VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && dq_accum && delta, "vs_attention_bwd: null pointer");
   VS_CHECK_ARG(((uintptr_t)ctx % 32 == 0) && ((uintptr_t)dctx % 32 == 0) && ((uintptr_t)dqkv % 32 == 0),
                "vs_attention_bwd: ctx / dctx / dqkv must be 32-byte aligned");
   VS_CHECK_ARG(B > 0 && N > 0 && H > 0, "vs_attention_bwd: bad shape");
@@ -587,11 +601,15 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   VS_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * N * D * sizeof(float), st));
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
-  (void)delta;  // kept in the ABI for callers that pre-allocated it; delta is computed inside the kernel
+  {
+    const long long rows = (long long)B * N * H;
+    attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)ctx,
+                                                                      (const __nv_bfloat16*)dctx, delta, B, N, H);
+    VS_CHECK_LAUNCH();
+  }
   dim3 grid((N + kKB - 1) / kKB, H, B);
-  attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tkv, tq, tdo, (const __nv_bfloat16*)ctx,
-                                                                  (const __nv_bfloat16*)dctx, lse,
-                                                                  (__nv_bfloat16*)dqkv, dq_accum, B, N, H, scale, dc);
+  attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv,
+                                                                  dq_accum, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }

@@ -156,7 +156,7 @@ def attention_fwd(qkv, ctx, lse, B, N, H, scale, dropout=None):
 
 def attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_accum, delta, B, N, H, scale, dropout=None):
     require_cuda(qkv, "attention_bwd")
-    _count(1)
+    _count(2)
     check(_lib.load().vs_attention_bwd(ptr(qkv), ptr(ctx), ptr(dctx), ptr(lse), ptr(dqkv), ptr(dq_accum), ptr(delta), B,
                                       N, H, scale, *_drop(dropout), stream()), "vs_attention_bwd")
 
