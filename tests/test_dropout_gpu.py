@@ -152,7 +152,8 @@ def test_module_train_eval_dropout_semantics():
     assert abs(l1.item() - l3.item()) < 1e-5 * abs(l1.item())   # float atomics in the loss reduction
     for k, p in m.named_parameters():
         if p.grad is not None:
-            assert _rel(p.grad, g1[k]) < 1e-3, k   # atomics reorder sums: not bitwise
+            # atomics reorder sums: not bitwise; key biases have a zero true gradient, hence the absolute floor
+            assert (p.grad - g1[k]).abs().max().item() <= 1e-3 * g1[k].abs().max().item() + 1e-5, k
     with torch.no_grad():
         m.eval()
         lo = m._loss(x, y).item()
