@@ -48,199 +48,233 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c32,
 // ================================================================================================
 // forward
 // ================================================================================================
+// One CTA per (128-query tile, head, batch); key blocks of 64 with double-buffered K / V stages; three CTAs per SM
+// (64 KB smem, 128 TMEM columns each).  8 softmax warps: warp w owns TMEM lane quadrant (w & 3) — query rows — and
+// half (w >> 2) of the 64 key columns of S and of the 64 head-dim columns of O; the two threads of a row exchange
+// their partial row maxima through smem once per key block.  (The first version — 128-key blocks, 4 softmax warps,
+// 2 CTAs/SM — left each SM with 8 latency-bound warps.)
+constexpr int kFKB = 64;
 struct AttnFwdSmem {
-  static constexpr int kQ = 0;
-  static constexpr int kK = 16384;
-  static constexpr int kV = 32768;
-  static constexpr int kP = 49152;             // 32 KB
-  static constexpr int kBar = 49152 + 32768;   // barriers
+  static constexpr int kQ = 0;                 // 128 x 128 B
+  static constexpr int kK = 16384;             // 2 stages x 64 x 128 B
+  static constexpr int kV = 32768;             // 2 stages x 64 x 128 B
+  static constexpr int kP = 49152;             // 128 x 128 B
+  static constexpr int kMax = 65536;           // float [2][2][128] partial row maxima (double-buffered by block)
+  static constexpr int kBar = 65536 + 2048;
   static constexpr int kTotal = kBar + 128 + 1024;
 };
+constexpr int kFwdThreads = 288;
 
-__global__ void __launch_bounds__(160, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
-                float* __restrict__ lse, int B, int N, int H, float scale, const DropCfg drop) {
+__global__ void __launch_bounds__(kFwdThreads, 3)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
+                const DropCfg drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::kBar);
-  uint64_t* bar_k = bars + 0;
-  uint64_t* bar_v = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_k = bars + 0;   // [2]
+  uint64_t* bar_v = bars + 2;   // [2]
+  uint64_t* bar_s = bars + 4;
+  uint64_t* bar_p = bars + 5;
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kDH;
-  const int nblk = (N + kBKV - 1) / kBKV;
+  const int nblk = (N + kFKB - 1) / kFKB;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmap_qkv);
-      mbar_init(bar_k, 1);
-      mbar_init(bar_v, 1);
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_kv);
+      for (int i = 0; i < 2; ++i) { mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); }
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128);
+      mbar_init(bar_p, 256);
       mbar_init(bar_o, 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
 
-  if (warp == 4) {
-    // control warp: converged, the elected lane issues TMA / MMA (keeps descriptors in uniform registers)
+  if (warp == 8) {
+    // ---------------------------------------------------------------- control warp (converged; elected lane issues)
     uint8_t* sQ = smem + AttnFwdSmem::kQ;
     uint8_t* sK = smem + AttnFwdSmem::kK;
     uint8_t* sV = smem + AttnFwdSmem::kV;
-    uint8_t* sP = smem + AttnFwdSmem::kP;
+    const uint32_t aP = smem_u32(smem + AttnFwdSmem::kP);
+    auto ncols_of = [&](int j) { return min(kFKB, ((N - j * kFKB) + 15) & ~15); };
+    auto issue_s = [&](int j) {   // S_j = Q K_j^T into TMEM cols [0, 64)
+      const uint32_t idesc = umma_idesc_bf16(kBQ, ncols_of(j), 0, 0);
+      const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t bd = umma_desc_sw128(smem_u32(sK) + (j & 1) * 8192, 16, 1024);
+#pragma unroll
+      for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc, k > 0);
+      umma_commit(bar_s);
+    };
     if (elect_one()) {
-      mbar_expect_tx(bar_k, 2 * 16384);
-      tma_load_3d(sQ, &tmap_qkv, bar_k, h * kDH, q0, b);
-      tma_load_3d(sK, &tmap_qkv, bar_k, D + h * kDH, 0, b);
-      mbar_expect_tx(bar_v, 16384);
-      tma_load_3d(sV, &tmap_qkv, bar_v, 2 * D + h * kDH, 0, b);
+      mbar_expect_tx(&bar_k[0], 16384 + 8192);
+      tma_load_3d(sQ, &tmap_q, &bar_k[0], h * kDH, q0, b);
+      tma_load_3d(sK, &tmap_kv, &bar_k[0], D + h * kDH, 0, b);
+      mbar_expect_tx(&bar_v[0], 8192);
+      tma_load_3d(sV, &tmap_kv, &bar_v[0], 2 * D + h * kDH, 0, b);
+      if (nblk > 1) {
+        mbar_expect_tx(&bar_k[1], 8192);
+        tma_load_3d(sK + 8192, &tmap_kv, &bar_k[1], D + h * kDH, kFKB, b);
+        mbar_expect_tx(&bar_v[1], 8192);
+        tma_load_3d(sV + 8192, &tmap_kv, &bar_v[1], 2 * D + h * kDH, kFKB, b);
+      }
     }
+    __syncwarp();
+    mbar_wait(&bar_k[0], 0);
+    tc_fence_after();
+    if (elect_one()) issue_s(0);
     __syncwarp();
     for (int j = 0; j < nblk; ++j) {
       const uint32_t ph = j & 1;
-      const int kv0 = j * kBKV;
-      const int ncols = min(kBKV, ((N - kv0) + 15) & ~15);
-      mbar_wait(bar_k, ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
-        const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-        const uint64_t bd = umma_desc_sw128(smem_u32(sK), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc, k > 0);
-        umma_commit(bar_s);
-      }
-      __syncwarp();
-      // K_j is free once S is complete: prefetch K_{j+1}
+      const int st = j & 1;
+      const uint32_t kph = (j >> 1) & 1;
+      // S_j complete -> K stage st is free: prefetch K_{j+2}
       mbar_wait(bar_s, ph);
-      if (j + 1 < nblk && elect_one()) {
-        mbar_expect_tx(bar_k, 16384);
-        tma_load_3d(sK, &tmap_qkv, bar_k, D + h * kDH, kv0 + kBKV, b);
+      if (j + 2 < nblk && elect_one()) {
+        mbar_expect_tx(&bar_k[st], 8192);
+        tma_load_3d(sK + st * 8192, &tmap_kv, &bar_k[st], D + h * kDH, (j + 2) * kFKB, b);
       }
       __syncwarp();
-      mbar_wait(bar_p, ph);
-      mbar_wait(bar_v, ph);
+      mbar_wait(bar_p, ph);           // P_j in smem, S_j consumed
+      mbar_wait(&bar_v[st], kph);
       tc_fence_after();
       if (elect_one()) {
+        const int ncols = ncols_of(j);
         const uint32_t idesc = umma_idesc_bf16(kBQ, kDH, 0, 1);
         for (int kk = 0; kk < ncols / 16; ++kk) {
-          const uint64_t ad = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(smem_u32(sV) + kk * 2048, 16384, 1024);
+          const uint64_t ad = umma_desc_sw128(aP + kk * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(smem_u32(sV) + st * 8192 + kk * 2048, 16384, 1024);
           umma_bf16(tmem_o, ad, bd, idesc, kk > 0);
         }
         umma_commit(bar_o);
       }
       __syncwarp();
-      mbar_wait(bar_o, ph);
-      if (j + 1 < nblk && elect_one()) {
-        mbar_expect_tx(bar_v, 16384);
-        tma_load_3d(sV, &tmap_qkv, bar_v, 2 * D + h * kDH, kv0 + kBKV, b);
+      if (j + 1 < nblk) {             // S_{j+1} right behind PV_j: ready when the softmax warps come back
+        mbar_wait(&bar_k[st ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) issue_s(j + 1);
+        __syncwarp();
+      }
+      mbar_wait(bar_o, ph);           // PV_j complete -> V stage st is free: prefetch V_{j+2}
+      if (j + 2 < nblk && elect_one()) {
+        mbar_expect_tx(&bar_v[st], 8192);
+        tma_load_3d(sV + st * 8192, &tmap_kv, &bar_v[st], 2 * D + h * kDH, (j + 2) * kFKB, b);
       }
       __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- softmax warps
-    const int r = warp * 32 + lane;
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
     const int q = q0 + r;
-    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    const uint32_t lane_off = uint32_t(quad * 32) << 16;
     uint8_t* sP = smem + AttnFwdSmem::kP;
+    float* s_max = reinterpret_cast<float*>(smem + AttnFwdSmem::kMax);   // [block parity][half][row]
     const float sl2 = scale * kLog2e;
     const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
     const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);  // pair index base
     float m_run = -INFINITY, l_run = 0.0f;
-    float o_acc[kDH];
+    float o_acc[32];
 #pragma unroll
-    for (int i = 0; i < kDH; ++i) o_acc[i] = 0.0f;
+    for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
 
     for (int j = 0; j < nblk; ++j) {
       const uint32_t ph = j & 1;
-      const int kv0 = j * kBKV;
-      const int nvalid = min(kBKV, N - kv0);
-      const int ncols = (nvalid + 15) & ~15;
+      const int kv0 = j * kFKB;
+      const int nvalid = min(kFKB, N - kv0);
       mbar_wait(bar_s, ph);
       tc_fence_after();
-      // pass 1: row max
-      float m_blk = -INFINITY;
-      for (int c = 0; c < ncols; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + lane_off + c, v);
-        tmem_ld_wait();
+      // this thread's 32 key columns of S_j
+      float sc[32];
+      float m_part = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < nvalid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 32 + cc * 16;
+        uint32_t v[16];
+        if (c < ((nvalid + 15) & ~15)) {
+          tmem_ld16(tmem_s + lane_off + c, v);
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x = (c + i < nvalid) ? __uint_as_float(v[i]) * sl2 : -INFINITY;
+          sc[cc * 16 + i] = x;
+          m_part = fmaxf(m_part, x);
+        }
       }
-      const float m_new = fmaxf(m_run, m_blk * sl2);
+      s_max[(ph * 2 + half) * 128 + r] = m_part;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m_new = fmaxf(m_run, fmaxf(m_part, s_max[(ph * 2 + (half ^ 1)) * 128 + r]));
       const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block (m_run = -inf)
       float l_blk = 0.0f;
-      // pass 2: probabilities -> bf16 smem (A operand of P·V)
-      for (int c = 0; c < ncols; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + lane_off + c, v);
-        tmem_ld_wait();
-        float f[32];
+      uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pv = (c + i < nvalid) ? ex2_approx(__uint_as_float(v[i]) * sl2 - m_new) : 0.0f;
-          l_blk += pv;   // the softmax normaliser uses the un-dropped probabilities (dropout acts on softmax output)
-          f[i] = pv;
-        }
-        if (drop.thresh != 0u) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {   // keys 2k, 2k+1 of a query row share one hash
-            bool k0, k1;
-            drop_keep2(2u * (drow + (uint32_t)((kv0 + c + i) >> 1)), dseed, drop.thresh, k0, k1);
-            f[i] = k0 ? f[i] * drop.scale : 0.0f;
-            f[i + 1] = k1 ? f[i + 1] * drop.scale : 0.0f;
-          }
-        }
-        store_row32_sw128(sP, r, c >> 5, f);
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2_approx(sc[i] - m_new), p1 = ex2_approx(sc[i + 1] - m_new);
+        l_blk += p0 + p1;   // the normaliser uses the un-dropped probabilities (dropout acts on softmax output)
+        bool k0 = true, k1 = true;
+        if (drop.thresh != 0u)   // keys 2k, 2k+1 of a query row share one hash
+          drop_keep2(2u * (drow + (uint32_t)((kv0 + half * 32 + i) >> 1)), dseed, drop.thresh, k0, k1);
+        pk[i >> 1] = pack_bf16(k0 ? p0 * dscale : 0.0f, k1 ? p1 * dscale : 0.0f);
       }
+      // P_j -> bf16 smem (A operand of P·V): this thread's 32 keys = 4 x 16-byte slots of its 128-byte row
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl)
+        *reinterpret_cast<uint4*>(sP + sw128_offset(r, half * 4 + sl)) =
+            make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
-      // O_j
+      // O_j: this thread's 32 head-dim columns
       mbar_wait(bar_o, ph);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < kDH; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_o + lane_off + c, v);
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(tmem_o + lane_off + half * 32 + cc * 16, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * alpha + __uint_as_float(v[i]);
+        for (int i = 0; i < 16; ++i) o_acc[cc * 16 + i] = o_acc[cc * 16 + i] * alpha + __uint_as_float(v[i]);
       }
       tc_fence_before();
     }
+    // total row sum = sum of the two column halves
+    float* s_l = s_max;   // reuse: all reads of s_max completed before the last bar_p / bar_o round trip
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    s_l[half * 128 + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_run + s_l[(half ^ 1) * 128 + r];
     if (q < N) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH;
+      const float inv = 1.0f / l_tot;
+      __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH + half * 32;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         u32x8 o;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16(o_acc[16 * i + 2 * j] * inv, o_acc[16 * i + 2 * j + 1] * inv);
+        for (int k = 0; k < 8; ++k) o.v[k] = pack_bf16(o_acc[16 * i + 2 * k] * inv, o_acc[16 * i + 2 * k + 1] * inv);
         st_global_256(dst + 16 * i, o);
       }
-      if (lse != nullptr) lse[((size_t)b * H + h) * N + q] = (m_run + log2f(l_run)) * kLn2;
+      if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * N + q] = (m_run + log2f(l_tot)) * kLn2;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 8) tmem_dealloc(tmem_base, 128);
 }
 
 // ================================================================================================
@@ -556,8 +590,10 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   VS_CHECK_ARG(B > 0 && N > 0 && H > 0, "vs_attention_fwd: bad shape");
   VS_CHECK_ARG(B <= 65535 && H <= 65535, "vs_attention_fwd: B/H exceed grid limits");
   VS_CHECK_ARG(sm_count() > 0, "vs_attention_fwd: no CUDA device");
-  CUtensorMap tm;
+  CUtensorMap tm, tkv;
   int rc = make_tok_tmap(&tm, qkv, B, N, 3 * H * kDH);
+  if (rc) return rc;
+  rc = make_tok_tmap(&tkv, qkv, B, N, 3 * H * kDH, kFKB);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
@@ -568,8 +604,8 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
-  attn_fwd_kernel<<<grid, 160, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, (__nv_bfloat16*)ctx, lse, B, N, H,
-                                                                           scale, dc);
+  attn_fwd_kernel<<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx, lse,
+                                                                                    B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
