@@ -15,6 +15,8 @@
 //   S = Q K^T, dP = dO V^T  ->  P = exp(S*scale - lse),  dS = P (dP - delta) scale      (registers -> smem, bf16)
 //   dV += P^T dO,  dK += dS^T Q   (TMEM accumulators over the query loop; P/dS/Q/dO read MN-major in place)
 //   dQ_i = dS K  -> fp32 atomics into dq_accum (one add per key block; converted to bf16 by the caller).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/vitseg.h"
 
@@ -65,7 +67,8 @@ struct AttnFwdSmem {
 };
 constexpr int kFwdThreads = 288;
 
-__global__ void __launch_bounds__(kFwdThreads, 3)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
                 const DropCfg drop) {
@@ -595,17 +598,24 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   if (rc) return rc;
   rc = make_tok_tmap(&tkv, qkv, B, N, 3 * H * kDH, kFKB);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static int occ = 0;
+  if (occ == 0) {
+    const char* e = getenv("VS_ATTN_FWD_OCC");   // tuning knob: resident CTAs per SM the kernel is compiled for
+    occ = (e && e[0] == '3') ? 3 : 2;
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        AttnFwdSmem::kTotal));
-    attr = true;
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnFwdSmem::kTotal));
   }
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
-  attn_fwd_kernel<<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx, lse,
-                                                                                    B, N, H, scale, dc);
+  if (occ == 3)
+    attn_fwd_kernel<3><<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx,
+                                                                                         lse, B, N, H, scale, dc);
+  else
+    attn_fwd_kernel<2><<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx,
+                                                                                         lse, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
