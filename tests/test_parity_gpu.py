@@ -282,3 +282,31 @@ def test_gradient_accumulation_matches_single_batch():
     for k, p in m.named_parameters():
         if p.grad is not None:
             assert _relmax(p.grad, full[k]) < 2e-2, k
+
+
+def test_fused_optimizer_updates_reach_the_kernels():
+    """torch.optim.Adam(fused=True) updates parameters without bumping Tensor._version: the bf16 weight shadows must
+    still follow (regression test: the first engine version keyed the re-cast on versions only and trained on stale
+    bf16 weights under fused optimizers / CUDA graphs)."""
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    dev = _dev()
+    cfg = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=128, num_hidden_layers=1, num_attention_heads=2)
+    sd = O.seeded_state_dict(cfg, 51, head_gain=2.0)
+    m = _build(LightningViTModel, cfg, sd, dev).train()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-3, fused=True)
+    x = O.synthetic_images(2, 224, seed=52)
+    y = O.synthetic_labels(2, 17, seed=53, size=224)
+    for _ in range(3):
+        loss = m._loss(x.to(dev), y.to(dev))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    m.eval()
+    now = {k[len("model."):]: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    assert max((now[k] - sd[k]).abs().max().item() for k in sd if "pooler" not in k) > 1e-3   # weights did move
+    with torch.no_grad():
+        ours = m(x.to(dev)).cpu()
+        ref = O.forward(now, x, cfg)
+        stale = O.forward(sd, x, cfg)
+    assert _relmax(ours, ref) < LOGIT_TOL
+    assert _relmax(stale, ref) > 5 * LOGIT_TOL    # the check would catch stale weights

@@ -101,7 +101,7 @@ class DataParallel:
         eng.ensure_packed(dev)
         if self.world > 1:
             dist.broadcast(eng.master, src=src, group=self.group)
-        eng._versions = None
+        eng._dirty = True
         self._synced = True
 
     def _attach(self):

@@ -44,7 +44,7 @@ class GraphedTrainStep:
         self.graph.replay()
         self.steps += 1
         for eng in self.engines:
-            eng._versions = None  # force a re-cast of the weight shadows on the next eager forward
+            eng._dirty = True  # force a re-cast of the weight shadows on the next eager forward
         return self.static_loss
 
     def __call__(self, batch: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
