@@ -228,6 +228,17 @@ int vs_cast_bf16_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int
 int vs_pack_conv3x3(const float* w, void* out, int32_t O, int32_t I, void* stream);
 int vs_unpack_conv3x3_grad(const float* g, float* dw, int32_t O, int32_t I, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused Adam / AdamW over the flat fp32 parameter arena (torch.optim.Adam / AdamW semantics, no amsgrad):
+ * one pass updates param / exp_avg / exp_avg_sq, writes the bf16 weight shadow and optionally zeroes grad.
+ * lr_dev / step_dev are DEVICE pointers (learning rate; 1-based step count) so captured graphs follow schedulers.
+ * Elements in [skip_begin, skip_end) are left untouched (parameters that never receive a gradient: the pooler).
+ * ------------------------------------------------------------------------------------------------ */
+int vs_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                 const float* lr_dev, const int32_t* step_dev, float beta1, float beta2, float eps, float weight_decay,
+                 int32_t decoupled, float grad_scale, int32_t zero_grad, int64_t skip_begin, int64_t skip_end,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

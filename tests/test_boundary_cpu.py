@@ -126,7 +126,7 @@ def test_compute_entry_fails_without_device():
     lib = _lib.load()
     d = _lib.GemmDesc()
     d.M = d.N = d.K = 128
-    d.A = d.B = d.out = 16
+    d.A = d.B = d.out = 64
     d.lda = d.ldb = d.ldo = 128
     rc = lib.vs_gemm_bf16(ctypes.byref(d), None)
     assert rc != 0

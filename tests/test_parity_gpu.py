@@ -310,3 +310,40 @@ def test_fused_optimizer_updates_reach_the_kernels():
         stale = O.forward(sd, x, cfg)
     assert _relmax(ours, ref) < LOGIT_TOL
     assert _relmax(stale, ref) > 5 * LOGIT_TOL    # the check would catch stale weights
+
+
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 0.01), (True, 0.01)])
+def test_fused_adam_matches_torch_adam(decoupled, wd):
+    """visiontransformer_b200.optim.FusedAdam (one pass over the flat arenas) against torch.optim.Adam / AdamW fed
+    the same gradients; the pooler (never receives a gradient) must stay untouched even with weight decay."""
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    from visiontransformer_b200.optim import FusedAdam
+    dev = _dev()
+    cfg = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=128, num_hidden_layers=1, num_attention_heads=2)
+    sd = O.seeded_state_dict(cfg, 61, head_gain=2.0)
+    a = _build(LightningViTModel, cfg, sd, dev).train()
+    b = _build(LightningViTModel, cfg, sd, dev).train()
+    opt_a = FusedAdam(a, lr=1e-3, weight_decay=wd, decoupled_weight_decay=decoupled)
+    cls = torch.optim.AdamW if decoupled else torch.optim.Adam
+    opt_b = cls(b.parameters(), lr=1e-3, weight_decay=wd)
+    x = O.synthetic_images(2, 224, seed=62).to(dev)
+    y = O.synthetic_labels(2, 17, seed=63, size=224).to(dev)
+    for step in range(4):
+        la = a._loss(x, y)
+        la.backward()
+        # feed b exactly a's gradients (isolates the optimizer arithmetic from kernel-level fp noise)
+        b.zero_grad(set_to_none=True)
+        for (_, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            pb.grad = None if pa.grad is None else pa.grad.clone()
+        opt_a.step()
+        opt_a.zero_grad()
+        opt_b.step()
+        for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert torch.allclose(pa, pb, rtol=2e-5, atol=2e-7), (step, k, (pa - pb).abs().max().item())
+    assert torch.equal(dict(a.named_parameters())["model.backbone.pooler.dense.weight"].cpu(),
+                       sd["backbone.pooler.dense.weight"])
+    # the bf16 shadow written by the fused pass is what the next forward uses
+    a.eval()
+    now = {k[len("model."):]: v.detach().cpu().clone() for k, v in a.state_dict().items()}
+    with torch.no_grad():
+        assert _relmax(a(x).cpu(), O.forward(now, x.cpu(), cfg)) < LOGIT_TOL

@@ -66,6 +66,8 @@ _SIGS = {
                            c_int, c_void_p],
     "vs_paed_multiclass_dense": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_int, c_int, c_void_p],
+    "vs_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_float, c_float,
+                     c_float, c_float, c_int, c_float, c_int, c_i64, c_i64, c_void_p],
     "vs_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "vs_cast_bf16_rows": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p],
     "vs_pack_conv3x3": [c_void_p, c_void_p, c_int, c_int, c_void_p],

@@ -545,3 +545,66 @@ extern "C" int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, int32_t 
   VS_CHECK_LAUNCH();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Fused Adam / AdamW over the flat parameter arena (model/CE/classes.py:296-297 Adam lr 1e-5;
+// model/PAED/classes.py:486-487 Adam, :536-548 AdamW).  One pass: reads p, g, m, v; writes p, m, v, the bf16 weight
+// shadow used by the tensor cores, and (optionally) zeroes g — replacing torch's multi-tensor Adam + the separate
+// cast pass + the gradient memset.  lr / step live in device memory so a captured CUDA graph sees schedulers.
+// ------------------------------------------------------------------------------------------------
+namespace vs {
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ lr_ptr,
+            const int* __restrict__ step_ptr, float beta1, float beta2, float eps, float wd, int decoupled,
+            float grad_scale, int zero_grad, long long skip_begin4, long long skip_end4) {
+  const float lr = lr_ptr[0];
+  const float t = (float)step_ptr[0];
+  const float bc1 = 1.0f - exp2f(t * log2f(beta1));
+  const float bc2 = 1.0f - exp2f(t * log2f(beta2));
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float decay = decoupled ? 1.0f - lr * wd : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    if (i < skip_begin4 || i >= skip_end4) {
+      float4 gv = reinterpret_cast<float4*>(g)[i];
+      float4 mv = reinterpret_cast<float4*>(m)[i];
+      float4 vv = reinterpret_cast<float4*>(v)[i];
+      float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float gg = gp[k] * grad_scale;
+        if (!decoupled) gg = fmaf(wd, pp[k], gg);
+        const float mm = fmaf(beta1, mp[k], (1.0f - beta1) * gg);
+        const float v2 = fmaf(beta2, vp[k], (1.0f - beta2) * gg * gg);
+        mp[k] = mm;
+        vp[k] = v2;
+        const float denom = sqrtf(v2) * inv_sqrt_bc2 + eps;
+        pp[k] = pp[k] * decay - step_size * (mm / denom);
+      }
+      reinterpret_cast<float4*>(p)[i] = pv;
+      reinterpret_cast<float4*>(m)[i] = mv;
+      reinterpret_cast<float4*>(v)[i] = vv;
+      if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16(pv.x, pv.y), pack_bf16(pv.z, pv.w));
+  }
+}
+}  // namespace vs
+
+extern "C" int vs_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                            const float* lr_dev, const int32_t* step_dev, float beta1, float beta2, float eps,
+                            float weight_decay, int32_t decoupled, float grad_scale, int32_t zero_grad,
+                            int64_t skip_begin, int64_t skip_end, void* stream) {
+  VS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && shadow_bf16 && lr_dev && step_dev, "vs_adam_step: null pointer");
+  VS_CHECK_ARG(n > 0 && n % 4 == 0 && skip_begin % 4 == 0 && skip_end % 4 == 0 && skip_begin <= skip_end,
+               "vs_adam_step: n and the skip range must be multiples of 4");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_adam_step: no CUDA device");
+  adam_kernel<<<nsm * 8, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16,
+                                                        n / 4, lr_dev, step_dev, beta1, beta2, eps, weight_decay,
+                                                        decoupled, grad_scale, zero_grad, skip_begin / 4, skip_end / 4);
+  VS_CHECK_LAUNCH();
+  return 0;
+}

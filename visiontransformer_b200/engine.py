@@ -77,6 +77,8 @@ class Engine:
         self.head_w_packed: Optional[torch.Tensor] = None
         self._versions = None
         self._dirty = True
+        self._shadow_fresh = False   # set by FusedAdam: shadow already matches the master arena
+        self._grads_zeroed = False   # set by FusedAdam: gradient arena already zero
         self._ws: Dict = {}
         self._saved = None
         self.grad_ready_hook = None  # callable(bucket_name) used by the data-parallel wrapper
@@ -144,6 +146,12 @@ class Engine:
         changed or a training forward happened since the last cast.  One pass over the arena: ~90 us for ViT-B/16."""
         params = self._named()
         versions = tuple(p._version for p in params.values())
+        if self._shadow_fresh and versions == self._versions:
+            # FusedAdam wrote the shadow (and re-packed the head weight) in its own pass
+            self._shadow_fresh = False
+            self._dirty = False
+            return
+        self._shadow_fresh = False
         if not train and not self._dirty and versions == self._versions:
             return
         self._dirty = train   # an optimizer step is expected to follow a training forward
@@ -151,6 +159,12 @@ class Engine:
         K.pack_conv3x3(self.w32("seg_head.0.weight"), self.head_w_packed)
         self.launches += 2
         self._versions = versions
+
+    def note_optimizer_step(self, grads_zeroed: bool):
+        """called by visiontransformer_b200.optim.FusedAdam after its fused update pass."""
+        self._shadow_fresh = True
+        self._grads_zeroed = grads_zeroed
+        self._versions = tuple(p._version for p in self._named().values())
 
     def w32(self, name):
         s = self.slots[name]
@@ -338,9 +352,10 @@ class Engine:
         params = self._named()
         base = self.grads.data_ptr()
         fresh = all(p.grad is None for p in params.values())
-        if fresh:
+        if fresh and not self._grads_zeroed:
             self.grads.zero_()
             self.launches += 1
+        self._grads_zeroed = False
         foreign = []
         for n, p in params.items():
             if n.startswith("backbone.pooler."):

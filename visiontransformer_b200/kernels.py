@@ -320,3 +320,12 @@ def unpack_conv3x3_grad(g, dw):
     O, I = dw.shape[0], dw.shape[1]
     _count(1)
     check(_lib.load().vs_unpack_conv3x3_grad(ptr(g), ptr(dw), O, I, stream()), "vs_unpack_conv3x3_grad")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, shadow, lr_dev, step_dev, beta1, beta2, eps, weight_decay, decoupled,
+              grad_scale, zero_grad, skip_begin, skip_end):
+    require_cuda(param, "adam_step")
+    _count(1)
+    check(_lib.load().vs_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(shadow), param.numel(),
+                                  ptr(lr_dev), ptr(step_dev), beta1, beta2, eps, weight_decay, int(decoupled),
+                                  grad_scale, int(zero_grad), skip_begin, skip_end, stream()), "vs_adam_step")
