@@ -281,7 +281,9 @@ def test_gradient_accumulation_matches_single_batch():
     (m._loss(x[2:], y[2:]) / 2).backward()
     for k, p in m.named_parameters():
         if p.grad is not None:
-            assert _relmax(p.grad, full[k]) < 2e-2, k
+            # absolute floor: key biases have an exactly-zero true gradient (softmax shift invariance)
+            err = (p.grad - full[k]).abs().max().item()
+            assert err <= 2e-2 * full[k].abs().max().item() + 2e-5, (k, err)
 
 
 def test_fused_optimizer_updates_reach_the_kernels():
