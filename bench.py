@@ -178,8 +178,13 @@ def run_ours(args):
     # reference defaults (model/CE/classes.py:233-234): hidden and attention dropout 0.1, active in train()
     lm = LightningViTModel(**MODEL, image_size=IMAGE, hidden_dropout_prob=args.dropout, attention_probs_dropout_prob=args.dropout)
     lm = lm.to(dev).train()
-    # model/CE/classes.py:296-297; capturable so that the whole step can live in one CUDA graph
-    opt = torch.optim.Adam(lm.parameters(), lr=1e-5, fused=True, capturable=True)
+    # Adam(lr=1e-5) of model/CE/classes.py:296-297, as the one-pass kernel over the flat arenas (update + bf16 weight
+    # shadow + gradient zeroing); --torch-adam uses torch.optim.Adam(fused, capturable) instead
+    if args.torch_adam:
+        opt = torch.optim.Adam(lm.parameters(), lr=1e-5, fused=True, capturable=True)
+    else:
+        from visiontransformer_b200.optim import FusedAdam
+        opt = FusedAdam(lm, lr=1e-5)
     dp = DataParallel(lm, opt)
     dp.broadcast_parameters()
 
@@ -321,7 +326,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "ViT-B/16 CE segmentation training, batch 64/GPU, 224x224, C=17 (BASELINE configs[1])",
-                       "global_batch": B * world, "parallelism": f"dp{world}", "optimizer": "Adam(lr=1e-5, fused, capturable) in timed region", "cuda_graph": graphed is not None,
+                       "global_batch": B * world, "parallelism": f"dp{world}", "optimizer": ("torch Adam(lr=1e-5, fused, capturable)" if args.torch_adam else "FusedAdam(lr=1e-5) = vs_adam_step") + " in timed region", "cuda_graph": graphed is not None,
                        "dropout": args.dropout, "l2": "working set (4.2 GB activations + 0.9 GB weights/grads per step) >> 126 MB L2; no flush needed",
                        "label_resize": "256->224 nearest inside the step, as LightningViTModel.training_step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -356,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam instead of the fused arena kernel")
     ap.add_argument("--dropout", type=float, default=0.1, help="hidden/attention dropout (reference default 0.1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
