@@ -307,10 +307,15 @@ def run_ours(args):
     tot_ms = sum(t for _, t in gemm_events)
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     roof = None
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic_r01.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, one ncu pass over this step
+        with open(tpath) as f:
+            traffic = float(json.load(f)["traffic_bytes_per_launch"])
     if tot_ms > 0:
         ach = tot_flops / (tot_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "vs::gemm_kernel (tcgen05, all variants)", "launches_timed": len(gemm_events), "timing": "CUDA events around each GEMM launch in 3 eager (non-graph) steps of the same workload",
+                "traffic": traffic, "traffic_unit": "bytes per launch (mean over the 149 GEMM launches of one step; profiles/gemm_traffic_r01.json)", "kernel": "vs::gemm_kernel (tcgen05, all variants)", "launches_timed": len(gemm_events), "timing": "CUDA events around each GEMM launch in 3 eager (non-graph) steps of the same workload",
                 "share_of_step": (tot_ms / 3) / (ms / args.steps), "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"}
     step_tflops = value * fl_img / 1e12
 
