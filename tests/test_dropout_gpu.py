@@ -88,7 +88,7 @@ def test_gemm_epilogue_dropout_and_layernorm_bwd_mask():
     assert _rel(z16, z) < 1e-2
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (1, 300, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (1, 300, 2), (1, 256, 2), (2, 40, 1)])
 def test_attention_dropout_forward_backward(B, N, H):
     from visiontransformer_b200 import kernels as K
     dev = _dev()

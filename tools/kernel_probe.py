@@ -193,6 +193,10 @@ def probe_attn():
     case(1, 128, 1)
     case(2, 197, 12)
     case(1, 64, 2)
+    case(2, 256, 2)      # largest single-pass forward
+    case(1, 17, 1)
+    case(3, 250, 3)
+    case(1, 257, 1)      # first streaming-forward length
     case(2, 577, 4)
     case(1, 1025, 2)
 

@@ -281,6 +281,199 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ================================================================================================
+// forward, short sequences (N <= 256: every 224x224 / patch-16 configuration, N = 197)
+// ================================================================================================
+// One CTA per (128-query tile, head, batch) sees ALL keys at once: S = Q K^T is ONE [128 x NK] accumulator
+// (NK = N rounded up to 16, <= 256 TMEM columns), so the softmax is a plain two-pass row softmax — no online rescale,
+// one max exchange and one P·V per CTA instead of one per 64-key block — and the key axis is padded to 16, not 64
+// (197 -> 208 instead of 256).  ncu r01 of the streaming kernel at N = 197: 40.5 M warp instructions, 56 % issue
+// utilisation, i.e. instruction-bound on padded / rescaled work.  O aliases the S columns once P is in smem; P
+// aliases the Q and K tiles.  101 KB smem + 256 TMEM columns -> two CTAs per SM.
+struct AttnFwdShortSmem {
+  static constexpr int kP = 0;                 // 4 x [128 x 128 B] (64 keys each), over Q, K and 16 KB more
+  static constexpr int kQ = 0;                 // 128 x 128 B
+  static constexpr int kK = 16384;             // up to 256 x 128 B
+  static constexpr int kV = 65536;             // up to 256 x 128 B
+  static constexpr int kRed = 98304;           // float [4][128]: partial maxima [2], partial sums [2]
+  static constexpr int kBar = 98304 + 2048;
+  static constexpr int kTotal = kBar + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                      __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
+                      const DropCfg drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdShortSmem::kBar);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * kDH;
+  const int NK = (N + 15) & ~15;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_kv);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- control warp
+    uint8_t* sQ = smem + AttnFwdShortSmem::kQ;
+    uint8_t* sK = smem + AttnFwdShortSmem::kK;
+    uint8_t* sV = smem + AttnFwdShortSmem::kV;
+    const uint32_t aP = smem_u32(smem + AttnFwdShortSmem::kP);
+    if (elect_one()) {
+      mbar_expect_tx(bar_qk, 16384 + NK * 128);
+      tma_load_3d(sQ, &tmap_q, bar_qk, h * kDH, q0, b);
+      tma_load_3d(sK, &tmap_kv, bar_qk, D + h * kDH, 0, b);
+      mbar_expect_tx(bar_v, NK * 128);
+      tma_load_3d(sV, &tmap_kv, bar_v, 2 * D + h * kDH, 0, b);
+    }
+    __syncwarp();
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    if (elect_one()) {   // S = Q K^T : [128 x NK], reduction over head_dim
+      const uint32_t idesc = umma_idesc_bf16(kBQ, NK, 0, 0);
+      const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t bd = umma_desc_sw128(smem_u32(sK), 16, 1024);
+#pragma unroll
+      for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, k > 0);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_p, 0);            // P in smem (over Q / K), S consumed
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    if (elect_one()) {   // O = P V : [128 x 64], reduction over the NK keys, into the (dead) S columns 0-63
+      const uint32_t idesc = umma_idesc_bf16(kBQ, kDH, 0, 1);
+      for (int kk = 0; kk < NK / 16; ++kk) {
+        const uint64_t ad = umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(smem_u32(sV) + kk * 2048, 16384, 1024);
+        umma_bf16(tmem_base, ad, bd, idesc, kk > 0);
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- softmax warps
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const int q = q0 + r;
+    const bool warp_live = q0 + quad * 32 < N;   // warps whose 32 query rows all lie beyond the sequence only sync
+    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16);
+    uint8_t* sP = smem + AttnFwdShortSmem::kP;
+    float* s_red = reinterpret_cast<float*>(smem + AttnFwdShortSmem::kRed);
+    const float sl2 = scale * kLog2e;
+    const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
+    const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);
+    // 16-column chunks [c_beg, c_end) of this thread's row: the two threads of a row split the key axis
+    const int nch = NK >> 4;
+    const int c_beg = half == 0 ? 0 : (nch + 1) >> 1;
+    const int c_end = half == 0 ? (nch + 1) >> 1 : nch;
+
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float m_part = -INFINITY;
+    if (warp_live) {
+      for (int c = c_beg; c < c_end; c += 2) {
+        uint32_t v0[16], v1[16];
+        const bool two = c + 1 < c_end;
+        tmem_ld16(taddr + c * 16, v0);
+        if (two) tmem_ld16(taddr + c * 16 + 16, v1);
+        tmem_ld_wait();
+        const int lim0 = N - c * 16, lim1 = N - (c + 1) * 16;   // valid columns in each chunk (>= 16: all)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (i < lim0) m_part = fmaxf(m_part, __uint_as_float(v0[i]));
+          if (two && i < lim1) m_part = fmaxf(m_part, __uint_as_float(v1[i]));
+        }
+      }
+      s_red[half * 128 + r] = m_part;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float l_part = 0.0f, m2 = 0.0f;
+    if (warp_live) {
+      m2 = fmaxf(m_part, s_red[(half ^ 1) * 128 + r]) * sl2;   // scale > 0: max(s) * c == max(s * c)
+      for (int c = c_beg; c < c_end; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        const int lim = N - c * 16;
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m2));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m2));
+          if (lim < 16) {   // zero-filled key rows give s = 0, not -inf
+            p0 = i < lim ? p0 : 0.0f;
+            p1 = i + 1 < lim ? p1 : 0.0f;
+          }
+          l_part += p0 + p1;   // the normaliser uses the un-dropped probabilities (dropout acts on softmax output)
+          bool k0 = true, k1 = true;
+          if (drop.thresh != 0u)   // keys 2k, 2k+1 of a query row share one hash
+            drop_keep2(2u * (drow + (uint32_t)((c * 16 + i) >> 1)), dseed, drop.thresh, k0, k1);
+          pk[i >> 1] = pack_bf16(k0 ? p0 * dscale : 0.0f, k1 ? p1 * dscale : 0.0f);
+        }
+        uint8_t* tile = sP + (c >> 2) * 16384;
+        const uint32_t slot = uint32_t(c & 3) * 2;
+        *reinterpret_cast<uint4*>(tile + sw128_offset(r, slot)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(tile + sw128_offset(r, slot + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      s_red[(2 + half) * 128 + r] = l_part;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    if (warp_live) {
+      const float l_tot = l_part + s_red[(2 + (half ^ 1)) * 128 + r];
+      uint32_t v[32];
+      tmem_ld32(taddr + half * 32, v);
+      tmem_ld_wait();
+      if (q < N) {
+        const float inv = 1.0f / l_tot;
+        __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH + half * 32;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          u32x8 o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            o.v[k] = pack_bf16(__uint_as_float(v[16 * i + 2 * k]) * inv, __uint_as_float(v[16 * i + 2 * k + 1]) * inv);
+          st_global_256(dst + 16 * i, o);
+        }
+        if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * N + q] = (m2 + log2f(l_tot)) * kLn2;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
+}
+
+// ================================================================================================
 // backward
 // ================================================================================================
 // ------------------------------------------------------------------------------------------------
@@ -596,6 +789,29 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   CUtensorMap tm, tkv;
   int rc = make_tok_tmap(&tm, qkv, B, N, 3 * H * kDH);
   if (rc) return rc;
+  static int force_stream = -1;
+  if (force_stream < 0) {
+    const char* e = getenv("VS_ATTN_FWD_STREAM");   // testing knob: 1 = always use the streaming kernel
+    force_stream = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (N <= 256 && !force_stream) {
+    // every key of a (batch, head) fits one accumulator: single-pass kernel
+    rc = make_tok_tmap(&tkv, qkv, B, N, 3 * H * kDH, (N + 15) & ~15);
+    if (rc) return rc;
+    static bool attr_short = false;
+    if (!attr_short) {
+      VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnFwdShortSmem::kTotal));
+      attr_short = true;
+    }
+    DropCfg dcs;
+    if (int rc2 = make_drop(&dcs, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
+    dim3 grid_s((N + kBQ - 1) / kBQ, H, B);
+    attn_fwd_short_kernel<<<grid_s, kFwdThreads, AttnFwdShortSmem::kTotal, (cudaStream_t)stream>>>(
+        tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dcs);
+    VS_CHECK_LAUNCH();
+    return 0;
+  }
   rc = make_tok_tmap(&tkv, qkv, B, N, 3 * H * kDH, kFKB);
   if (rc) return rc;
   static int occ = 0;
