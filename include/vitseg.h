@@ -99,14 +99,16 @@ int vs_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* out,
  * Backward: dx_out[M,D] (fp32) = dx_in (nullable: skip-connection gradient) + LN'(dy); dgamma/dbeta accumulate (+=).
  *   dy is bf16 or fp32 (dy_is_f32); dx_bf16 (nullable) receives a bf16 copy of dx_out, multiplied by the dropout
  *   mask of site `dropout_site` when dropout_p > 0 (it feeds the backward GEMMs of the projection whose output was
- *   dropped out in forward).
+ *   dropped out in forward).  dbias_colsum (nullable, fp32 [D], +=) receives the column sums of that bf16 output,
+ *   i.e. the bias gradient of that projection (autograd of nn.Linear bias) without a separate vs_colsum_bf16 pass.
+ *   All matrix operands must be 16-byte aligned (rows are streamed with cp.async.bulk).
  * ------------------------------------------------------------------------------------------------ */
 int vs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t M, int32_t D,
                      void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
 int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const float* gamma, const float* mean,
                      const float* rstd, const float* dx_in, int32_t M, int32_t D, float* dx_out, void* dx_bf16,
-                     float* dgamma, float* dbeta, float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site,
-                     void* stream);
+                     float* dgamma, float* dbeta, float* dbias_colsum, float dropout_p, const uint32_t* dropout_seed,
+                     uint32_t dropout_site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-head self-attention (TF:220-251 + sdpa_attention_forward): softmax(Q K^T * scale) V per (batch, head).

@@ -130,8 +130,8 @@ def probe_gemm():
 
 def probe_ln():
     def f():
-        for D in (768, 1024, 512):
-            M = 1000
+        # M = 12605 / 5003: more row groups than SMs x stages (ring reuse) and a ragged last group
+        for D, M in ((768, 1000), (1024, 1000), (512, 1000), (768, 12605), (128, 5003), (1024, 4099)):
             x = torch.randn(M, D, device=dev) * 2 + 0.5
             g = torch.randn(D, device=dev)
             b = torch.randn(D, device=dev)
@@ -141,7 +141,7 @@ def probe_ln():
             rstd = torch.empty(M, device=dev)
             K.layernorm_fwd(x, g, b, 1e-12, y, yf, mean, rstd)
             ref = F.layer_norm(x, (D,), g, b, 1e-12)
-            report(f"ln fwd f32 D{D}", rel(yf, ref), 1e-5)
+            report(f"ln fwd f32 D{D} M{M}", rel(yf, ref), 1e-5)
             report(f"ln fwd bf16 D{D}", rel(y, ref), 1e-2)
             xr = x.clone().requires_grad_(True)
             gr = g.clone().requires_grad_(True)
@@ -153,8 +153,11 @@ def probe_ln():
             dxb = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
             dg = torch.zeros(D, device=dev)
             db = torch.zeros(D, device=dev)
-            K.layernorm_bwd(dy, x, g, mean, rstd, dxin, dx, dxb, dg, db)
-            report(f"ln bwd dx D{D}", rel(dx, xr.grad + dxin), 1e-4)
+            dbias = torch.zeros(D, device=dev)
+            K.layernorm_bwd(dy, x, g, mean, rstd, dxin, dx, dxb, dg, db, dbias=dbias)
+            report(f"ln bwd dx D{D} M{M}", rel(dx, xr.grad + dxin), 1e-4)
+            report(f"ln bwd bf16 copy D{D}", rel(dxb, xr.grad + dxin), 1e-2)
+            report(f"ln bwd fused colsum D{D} M{M}", rel(dbias, (xr.grad + dxin).sum(0)), 1e-4)
             report(f"ln bwd dgamma D{D}", rel(dg, gr.grad), 1e-4)
             report(f"ln bwd dbeta D{D}", rel(db, br.grad), 1e-4)
             dyb = bf(dy)

@@ -41,7 +41,7 @@ _SIGS = {
     "vs_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p],
     "vs_layernorm_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                         c_void_p, c_void_p, c_void_p, c_float, c_void_p, C.c_uint32, c_void_p],
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, C.c_uint32, c_void_p],
     "vs_attention_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, C.c_uint32,
                          c_void_p],
     "vs_attention_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -403,7 +403,8 @@ class Engine:
         # the bf16 copy of dx feeds the backward GEMMs of the last layer's fc2, whose output was dropped out (site 2L)
         K.layernorm_bwd(ws["dtok"], ws["x_in"][L], self.w32("backbone.layernorm.weight"), fs[0], fs[1], None, dx,
                         ws["dx16"], self.g32("backbone.layernorm.weight"), self.g32("backbone.layernorm.bias"),
-                        dropout=self._site(p_hid, 2 * L) if L > 0 else None)
+                        dropout=self._site(p_hid, 2 * L) if L > 0 else None,
+                        dbias=self.g32(f"backbone.encoder.layer.{L - 1}.output.dense.bias") if L > 0 else None)
         n += 8
         if hook:
             hook("head")
@@ -411,8 +412,8 @@ class Engine:
         for i in reversed(range(L)):
             p = f"backbone.encoder.layer.{i}."
             st = ws["stats"][i]
-            # fc2: x_out = x_mid + h_act W2^T + b2
-            K.colsum(ws["dx16"], self.g32(p + "output.dense.bias"), accumulate=True)
+            # fc2: x_out = x_mid + h_act W2^T + b2   (its bias gradient = column sums of dx16: fused into the
+            # LayerNorm backward that produced dx16)
             K.gemm(ws["dx16"], ws["h_act"][i], self.g32(p + "output.dense.weight"), a_mn=True, b_mn=True,
                    accumulate=True)
             K.gemm(ws["dx16"], self.w16(p + "output.dense.weight"), ws["dh"], b_mn=True, aux=ws["h_pre"][i],
@@ -425,10 +426,10 @@ class Engine:
             # LN2 + skip
             K.layernorm_bwd(ws["d_ln"], ws["x_mid"][i], self.w32(p + "layernorm_after.weight"), st[2], st[3], dx,
                             dx_other, ws["dx16"], self.g32(p + "layernorm_after.weight"),
-                            self.g32(p + "layernorm_after.bias"), dropout=self._site(p_hid, 1 + 2 * i))
+                            self.g32(p + "layernorm_after.bias"), dropout=self._site(p_hid, 1 + 2 * i),
+                            dbias=self.g32(p + "attention.output.dense.bias"))
             dx, dx_other = dx_other, dx
             # attention output projection
-            K.colsum(ws["dx16"], self.g32(p + "attention.output.dense.bias"), accumulate=True)
             K.gemm(ws["dx16"], ws["ctx"][i], self.g32(p + "attention.output.dense.weight"), a_mn=True, b_mn=True,
                    accumulate=True)
             K.gemm(ws["dx16"], self.w16(p + "attention.output.dense.weight"), ws["dctx"], b_mn=True)
@@ -447,9 +448,10 @@ class Engine:
             K.layernorm_bwd(ws["d_ln"], ws["x_in"][i], self.w32(p + "layernorm_before.weight"), st[0], st[1], dx,
                             dx_other, ws["dx16"], self.g32(p + "layernorm_before.weight"),
                             self.g32(p + "layernorm_before.bias"),
-                            dropout=self._site(p_hid, 2 * i) if i > 0 else None)
+                            dropout=self._site(p_hid, 2 * i) if i > 0 else None,
+                            dbias=self.g32(f"backbone.encoder.layer.{i - 1}.output.dense.bias") if i > 0 else None)
             dx, dx_other = dx_other, dx
-            n += 19
+            n += 17
             if hook:
                 hook(f"layer{i}")
         # --- embeddings

@@ -135,13 +135,14 @@ def _drop(dropout):
     return float(dropout[0]), ptr(dropout[1]), int(dropout[2])
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_bf16, dgamma, dbeta, dropout=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_bf16, dgamma, dbeta, dropout=None, dbias=None):
     require_cuda(x, "layernorm_bwd")
     M, D = x.shape
     assert dy.is_contiguous() and dy.dtype in (BF16, F32)
     _count(1)
     check(_lib.load().vs_layernorm_bwd(ptr(dy), int(dy.dtype == F32), ptr(x), ptr(gamma), ptr(mean), ptr(rstd),
-                                      ptr(dx_in), M, D, ptr(dx_out), ptr(dx_bf16), ptr(dgamma), ptr(dbeta), *_drop(dropout),
+                                      ptr(dx_in), M, D, ptr(dx_out), ptr(dx_bf16), ptr(dgamma), ptr(dbeta), ptr(dbias),
+                                      *_drop(dropout),
                                       stream()),
           "vs_layernorm_bwd")
 
