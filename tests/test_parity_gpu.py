@@ -341,7 +341,10 @@ def test_fused_adam_matches_torch_adam(decoupled, wd):
         opt_a.zero_grad()
         opt_b.step()
         for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
-            assert torch.allclose(pa, pb, rtol=2e-5, atol=2e-7), (step, k, (pa - pb).abs().max().item())
+            # atol = 0.3 % of one update (lr 1e-3): with coupled weight decay an element whose gradient cancels
+            # wd * p (g' = g + wd p ~ 1e-8 from two 2.6e-5 terms) amplifies the fma-vs-mul/add rounding of g' to
+            # ~1e-6 in p — observed in 1 of 10 runs, position_embeddings idx 22664
+            assert torch.allclose(pa, pb, rtol=2e-5, atol=3e-6), (step, k, (pa - pb).abs().max().item())
     assert torch.equal(dict(a.named_parameters())["model.backbone.pooler.dense.weight"].cpu(),
                        sd["backbone.pooler.dense.weight"])
     # the bf16 shadow written by the fused pass is what the next forward uses
