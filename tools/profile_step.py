@@ -7,6 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from visiontransformer_b200.ce.classes import LightningViTModel  # noqa: E402
+from visiontransformer_b200.optim import FusedAdam  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
@@ -19,20 +20,21 @@ DROP = args.dropout
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 m = LightningViTModel(17, 16, 768, 12, 12, hidden_dropout_prob=DROP, attention_probs_dropout_prob=DROP).to(dev).train()
-opt = torch.optim.Adam(m.parameters(), lr=1e-5, fused=True)
+opt = FusedAdam(m, lr=1e-5)
 x = torch.rand(args.batch, 3, 224, 224, device=dev)
 y = torch.randint(0, 17, (args.batch, 256, 256), device=dev)
 for i in range(args.warmup + args.steps):
     if i == args.warmup:
         torch.cuda.synchronize()
-        torch.cuda.nvtx.range_push("profiled")
+        torch.cuda.profiler.start()   # process-wide (backward launches come from the autograd thread): ncu --profile-from-start off
     if args.mode == "train":
         loss = m.training_step((x, y), i)
         loss.backward()
         opt.step()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
     else:
         with torch.no_grad():
             m.model.predict_mask(x)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done", float(loss) if args.mode == "train" else "")

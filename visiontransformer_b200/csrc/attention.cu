@@ -397,44 +397,63 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     tc_fence_after();
     float m_part = -INFINITY;
     if (warp_live) {
+      // pass 1: row maximum.  Only the chunk that straddles N needs per-column masking (warp-uniform branch).
       for (int c = c_beg; c < c_end; c += 2) {
         uint32_t v0[16], v1[16];
         const bool two = c + 1 < c_end;
         tmem_ld16(taddr + c * 16, v0);
         if (two) tmem_ld16(taddr + c * 16 + 16, v1);
         tmem_ld_wait();
-        const int lim0 = N - c * 16, lim1 = N - (c + 1) * 16;   // valid columns in each chunk (>= 16: all)
+        const int lim0 = N - c * 16, lim1 = N - (c + 1) * 16;   // valid columns of each chunk (>= 16: all)
+        if (lim0 >= 16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < lim0) m_part = fmaxf(m_part, __uint_as_float(v0[i]));
-          if (two && i < lim1) m_part = fmaxf(m_part, __uint_as_float(v1[i]));
+          for (int i = 0; i < 16; ++i) m_part = fmaxf(m_part, __uint_as_float(v0[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < lim0) m_part = fmaxf(m_part, __uint_as_float(v0[i]));
+        }
+        if (two) {
+          if (lim1 >= 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m_part = fmaxf(m_part, __uint_as_float(v1[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < lim1) m_part = fmaxf(m_part, __uint_as_float(v1[i]));
+          }
         }
       }
       s_red[half * 128 + r] = m_part;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    // pass 2: p' = exp2(s*c - m) * dscale with the dropout scale folded into the exponent; the row sum is kept in
+    // the same scaled units (the normaliser uses the un-dropped probabilities: dropout acts on the softmax output)
     float l_part = 0.0f, m2 = 0.0f;
+    const float lds = log2f(dscale);
     if (warp_live) {
       m2 = fmaxf(m_part, s_red[(half ^ 1) * 128 + r]) * sl2;   // scale > 0: max(s) * c == max(s * c)
+      const float m2s = m2 - lds;
       for (int c = c_beg; c < c_end; ++c) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
         tmem_ld_wait();
         const int lim = N - c * 16;
+        float pe[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pe[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m2s));
+        if (lim < 16) {   // zero-filled key rows give s = 0, not -inf
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pe[i] = i < lim ? pe[i] : 0.0f;
+        }
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m2));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m2));
-          if (lim < 16) {   // zero-filled key rows give s = 0, not -inf
-            p0 = i < lim ? p0 : 0.0f;
-            p1 = i + 1 < lim ? p1 : 0.0f;
-          }
-          l_part += p0 + p1;   // the normaliser uses the un-dropped probabilities (dropout acts on softmax output)
+          l_part += pe[i] + pe[i + 1];
           bool k0 = true, k1 = true;
           if (drop.thresh != 0u)   // keys 2k, 2k+1 of a query row share one hash
             drop_keep2(2u * (drow + (uint32_t)((c * 16 + i) >> 1)), dseed, drop.thresh, k0, k1);
-          pk[i >> 1] = pack_bf16(k0 ? p0 * dscale : 0.0f, k1 ? p1 * dscale : 0.0f);
+          pk[i >> 1] = pack_bf16(k0 ? pe[i] : 0.0f, k1 ? pe[i + 1] : 0.0f);
         }
         uint8_t* tile = sP + (c >> 2) * 16384;
         const uint32_t slot = uint32_t(c & 3) * 2;
@@ -454,7 +473,8 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       tmem_ld32(taddr + half * 32, v);
       tmem_ld_wait();
       if (q < N) {
-        const float inv = 1.0f / l_tot;
+        // l_tot and the accumulator are both in dropout-scaled units: O = acc * dscale / l_tot, l = l_tot / dscale
+        const float inv = dscale / l_tot;
         __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH + half * 32;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -464,7 +484,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             o.v[k] = pack_bf16(__uint_as_float(v[16 * i + 2 * k]) * inv, __uint_as_float(v[16 * i + 2 * k + 1]) * inv);
           st_global_256(dst + 16 * i, o);
         }
-        if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * N + q] = (m2 + log2f(l_tot)) * kLn2;
+        if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * N + q] = (m2 + log2f(l_tot) - lds) * kLn2;
       }
     }
   }
