@@ -352,3 +352,44 @@ def test_fused_adam_matches_torch_adam(decoupled, wd):
     now = {k[len("model."):]: v.detach().cpu().clone() for k, v in a.state_dict().items()}
     with torch.no_grad():
         assert _relmax(a(x).cpu(), O.forward(now, x.cpu(), cfg)) < LOGIT_TOL
+
+
+def test_graphed_train_step_matches_eager_and_honours_set_lr():
+    """GraphedTrainStep (whole step in one CUDA graph) follows the eager trajectory, and FusedAdam.set_lr reaches an
+    already captured graph (the lr lives in pinned host memory that the replayed copy node re-reads)."""
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    from visiontransformer_b200.graph import GraphedTrainStep
+    from visiontransformer_b200.optim import FusedAdam
+    dev = _dev()
+    cfg = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=128, num_hidden_layers=2, num_attention_heads=2)
+    sd = O.seeded_state_dict(cfg, 71, head_gain=2.0)
+    x = O.synthetic_images(2, 224, seed=72).to(dev)
+    y = O.synthetic_labels(2, 17, seed=73, size=224).to(dev)
+
+    def make():
+        m = _build(LightningViTModel, cfg, sd, dev).train()
+        opt = FusedAdam(m, lr=1e-3)
+
+        def step(batch, i):
+            loss = m._loss(*batch)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            return loss.detach()
+        return m, opt, step
+
+    a, _, step_a = make()
+    eager = [step_a((x, y), i).item() for i in range(4)]
+    b, opt_b, step_b = make()
+    g = GraphedTrainStep(step_b, (x, y), warmup=1, engines=[b.model.engine])     # eager step 0, then capture
+    replayed = [g((x, y)).item() for _ in range(3)]                              # steps 1..3
+    for le, lr_ in zip(eager[1:], replayed):
+        assert abs(le - lr_) <= 2e-3 * abs(le), (eager, replayed)
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=0, atol=2e-4), (k, (pa - pb).abs().max().item())   # 4 steps of lr 1e-3
+    opt_b.set_lr(0.0)
+    before = {k: p.detach().clone() for k, p in b.named_parameters()}
+    g((x, y))
+    torch.cuda.synchronize()
+    for k, p in b.named_parameters():
+        assert torch.equal(p, before[k]), k

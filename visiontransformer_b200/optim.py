@@ -59,6 +59,14 @@ class FusedAdam(torch.optim.Optimizer):
         eng.note_optimizer_step(grads_zeroed=True)
         return loss
 
+    def set_lr(self, lr: float):
+        """Changes the learning rate; also effective for an already captured CUDA graph (the replayed host->device
+        copy re-reads this pinned value)."""
+        for group in self.param_groups:
+            group["lr"] = float(lr)
+        if self._lr_host is not None:
+            self._lr_host[0] = float(lr)
+
     def zero_grad(self, set_to_none: bool = True):
         # the arena was zeroed by the update kernel; dropping the views makes the next backward re-attach them
         for group in self.param_groups:
