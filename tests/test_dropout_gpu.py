@@ -149,11 +149,13 @@ def test_module_train_eval_dropout_semantics():
     l3 = m.training_step((x, y), 2)              # same counter -> identical result
     l3.backward()
     assert torch.isfinite(l1) and l1.item() != l2.item()
-    assert abs(l1.item() - l3.item()) < 1e-5 * abs(l1.item())   # float atomics in the loss reduction
+    assert abs(l1.item() - l3.item()) < 1e-4 * abs(l1.item())   # float atomics in the loss reduction
     for k, p in m.named_parameters():
         if p.grad is not None:
             # atomics reorder sums: not bitwise; key biases have a zero true gradient, hence the absolute floor
-            assert (p.grad - g1[k]).abs().max().item() <= 1e-3 * g1[k].abs().max().item() + 1e-5, k
+            # (dQ is accumulated with fp32 atomics and then rounded to bf16: a reordered sum flips single roundings,
+            #  2^-9 relative on those elements, which the earlier layers inherit)
+            assert (p.grad - g1[k]).abs().max().item() <= 5e-3 * g1[k].abs().max().item() + 1e-5, k
     with torch.no_grad():
         m.eval()
         lo = m._loss(x, y).item()
