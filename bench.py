@@ -170,6 +170,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's version / debug banner goes to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = BATCH_PER_GPU
     C = MODEL["num_classes"]
@@ -340,7 +342,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "model_tflops": {"achieved": step_tflops, "frac_of_sustained_peak": step_tflops / peak_tf,
+            "model_tflops": {"achieved": step_tflops, "frac_of_sustained_peak": step_tflops / (peak_tf * world),
                              "flops_per_image": fl_img, "note": "whole training step, 3x forward FLOPs (BASELINE.md §4)"},
             "inference": {"logits_images_per_sec": world * B * n_inf / (ms_inf / 1e3),
                           "mask_images_per_sec": world * B * n_inf / (ms_mask / 1e3), "batch": B,

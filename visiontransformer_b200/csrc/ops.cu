@@ -22,7 +22,25 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int M, int N, 
   if (col < N) {
     const int rows_per = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-    for (int r = r0 + rl; r < r1; r += 8) {
+    // four independent 16-byte loads in flight per thread: the inputs are L2-resident (just written by the producing
+    // GEMM), so the loop is bound by load latency, not bandwidth
+    int r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (long long)(r + 8 * u) * ldx + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(w[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
       const uint4 v = *reinterpret_cast<const uint4*>(x + (long long)r * ldx + col);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
