@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/dp_check.py : data-parallel equivalence on real GPUs (NCCL).
+"""torchrun --nproc-per-node N tests/dp_check_nccl.py : data-parallel equivalence on real GPUs (NCCL).
 N ranks each train on their shard of a global batch; rank 0 also trains a single-process replica on the whole
 batch; losses and post-step weights must agree (CE: averaged grads; PAEDTrainer: global-batch loss, summed grads)."""
 import os

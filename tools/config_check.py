@@ -9,7 +9,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import vitseg_oracle as O  # noqa: E402  (synthetic targets only)
+from _synth import binary_targets  # noqa: E402
 from visiontransformer_b200.ce.classes import LightningViTModel  # noqa: E402
 from visiontransformer_b200.graph import GraphedTrainStep  # noqa: E402
 from visiontransformer_b200.model import flops_per_image  # noqa: E402
@@ -56,7 +56,7 @@ which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
 if "cfg3" in which:
     B = 64
     x = torch.rand(B, 3, 224, 224, device=dev)
-    masks, se, si = [t.to(dev) for t in O.synthetic_binary_targets(B, 224, seed=3)]
+    masks, se, si = [t.to(dev) for t in binary_targets(B, 224, seed=3)]
     m = PAEDTrainer(1, 16, 768, 12, 12).to(dev).train()
     train_case("cfg3 ViT-B/16 PAEDTrainer (BCE+Dice+|PAED|), B=64", m, FusedAdamW(m, lr=1e-4), (x, masks, se, si), B)
     del m

@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import vitseg_oracle as O  # noqa: E402  (synthetic targets only)
+from _synth import binary_targets  # noqa: E402
 from visiontransformer_b200 import losses as LS  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -15,7 +15,7 @@ torch.manual_seed(0)
 low = torch.randn(B, C, g, g, device=dev, requires_grad=True)
 y = torch.randint(0, C, (B, S, S), device=dev)
 low1 = torch.randn(B, 1, g, g, device=dev, requires_grad=True)
-masks, se, si = [t.to(dev) for t in O.synthetic_binary_targets(B, S, seed=3)]
+masks, se, si = [t.to(dev) for t in binary_targets(B, S, seed=3)]
 
 
 def t(name, fn, reps=10):
