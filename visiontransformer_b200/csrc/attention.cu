@@ -561,14 +561,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
   uint64_t* bar_pds = bars + 3;
   uint64_t* bar_dq = bars + 4;
   uint64_t* bar_dqr = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_epi = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * kKB, h = blockIdx.y, b = blockIdx.z;
   const int D = H * kDH;
   const int nq = (N + kBQ - 1) / kBQ;
-  const int nvalid_kv = min(kKB, N - kv0);
-  const int ncols = (nvalid_kv + 15) & ~15;
+  const int nkb = (N + kKB - 1) / kKB;
+  // Persistent CTAs: work item w = ((b * H + h) * nkb + key block); the key blocks of one (batch, head) are adjacent so
+  // that their Q / dO tiles are L2 hits.  Barrier setup, the TMEM allocation and the parameter / tensor-map fetches
+  // (9 % of the stall samples of the one-CTA-per-item version, ncu r01) happen once, and the next item's K / V / Q / dO
+  // loads overlap the dQ and dK / dV read-out of the current one.
+  const int total = B * H * nkb;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -581,6 +585,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
       mbar_init(bar_pds, 256);
       mbar_init(bar_dq, 1);
       mbar_init(bar_dqr, 256);
+      mbar_init(bar_epi, 256);
       fence_mbar_init();
     }
     __syncwarp();
@@ -601,69 +606,83 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
     uint8_t* sDO = smem + AttnBwdSmem::kDO;
     const uint32_t aP = smem_u32(smem + AttnBwdSmem::kP);
     const uint32_t aDS = smem_u32(smem + AttnBwdSmem::kDS);
-    if (elect_one()) {
+    auto load_item = [&](int w) {   // K / V block and the first Q / dO tile of work item w
+      const int kb = w % nkb, bh = w / nkb;
+      const int h = bh % H, b = bh / H;
       mbar_expect_tx(bar_kv, 2 * 8192);
-      tma_load_3d(sK, &tmap_kv, bar_kv, D + h * kDH, kv0, b);
-      tma_load_3d(sV, &tmap_kv, bar_kv, 2 * D + h * kDH, kv0, b);
+      tma_load_3d(sK, &tmap_kv, bar_kv, D + h * kDH, kb * kKB, b);
+      tma_load_3d(sV, &tmap_kv, bar_kv, 2 * D + h * kDH, kb * kKB, b);
       mbar_expect_tx(bar_q, 2 * 16384);
       tma_load_3d(sQ, &tmap_q, bar_q, h * kDH, 0, b);
       tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, 0, b);
-    }
+    };
+    if ((int)blockIdx.x < total && elect_one()) load_item(blockIdx.x);
     __syncwarp();
-    mbar_wait(bar_kv, 0);
-    for (int i = 0; i < nq; ++i) {
-      const uint32_t ph = i & 1;
-      mbar_wait(bar_q, ph);
-      if (i > 0) mbar_wait(bar_dqr, ph ^ 1);   // dQ_{i-1} (aliasing the S columns) has been read out
-      tc_fence_after();
-      if (elect_one()) {
-        // S = Q K^T and dP = dO V^T, both [128 q x ncols k], reduction over head_dim
-        const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
-        const uint64_t qd = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-        const uint64_t kd = umma_desc_sw128(smem_u32(sK), 16, 1024);
-        const uint64_t od = umma_desc_sw128(smem_u32(sDO), 16, 1024);
-        const uint64_t vd = umma_desc_sw128(smem_u32(sV), 16, 1024);
+    uint32_t it = 0, qn = 0;   // work items / query tiles processed so far by this CTA: barrier phase parities
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int kb = w % nkb, bh = w / nkb;
+      const int h = bh % H, b = bh / H;
+      const int ncols = (min(kKB, N - kb * kKB) + 15) & ~15;
+      mbar_wait(bar_kv, it & 1);
+      for (int i = 0; i < nq; ++i, ++qn) {
+        const uint32_t ph = qn & 1;
+        mbar_wait(bar_q, ph);
+        if (qn > 0) mbar_wait(bar_dqr, ph ^ 1);   // the previous dQ (aliasing the S columns) has been read out
+        tc_fence_after();
+        if (elect_one()) {
+          // S = Q K^T and dP = dO V^T, both [128 q x ncols k], reduction over head_dim
+          const uint32_t idesc = umma_idesc_bf16(kBQ, ncols, 0, 0);
+          const uint64_t qd = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+          const uint64_t kd = umma_desc_sw128(smem_u32(sK), 16, 1024);
+          const uint64_t od = umma_desc_sw128(smem_u32(sDO), 16, 1024);
+          const uint64_t vd = umma_desc_sw128(smem_u32(sV), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
+          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
 #pragma unroll
-        for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
-        umma_commit(bar_s);
-      }
-      __syncwarp();
-      mbar_wait(bar_pds, ph);
-      tc_fence_after();
-      if (elect_one()) {
-        // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 64 keys, K = 128 queries), B MN-major (N = 64)
-        const uint32_t idesc = umma_idesc_bf16(kKB, kDH, 1, 1);
-#pragma unroll
-        for (int kk = 0; kk < kBQ / 16; ++kk) {
-          const uint64_t pd = umma_desc_sw128(aP + kk * 2048, 16384, 1024);
-          const uint64_t dod = umma_desc_sw128(smem_u32(sDO) + kk * 2048, 16384, 1024);
-          umma_bf16(tm_dv, pd, dod, idesc, (i > 0 || kk > 0));
+          for (int k = 0; k < kDH / 16; ++k) umma_bf16(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
+          umma_commit(bar_s);
         }
+        __syncwarp();
+        mbar_wait(bar_pds, ph);
+        if (i == 0 && it > 0) mbar_wait(bar_epi, (it - 1) & 1);   // dK / dV of the previous item have been read out
+        tc_fence_after();
+        if (elect_one()) {
+          // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 64 keys, K = 128 queries), B MN-major (N = 64)
+          const uint32_t idesc = umma_idesc_bf16(kKB, kDH, 1, 1);
 #pragma unroll
-        for (int kk = 0; kk < kBQ / 16; ++kk) {
-          const uint64_t dsd = umma_desc_sw128(aDS + kk * 2048, 16384, 1024);
-          const uint64_t qd = umma_desc_sw128(smem_u32(sQ) + kk * 2048, 16384, 1024);
-          umma_bf16(tm_dk, dsd, qd, idesc, (i > 0 || kk > 0));
+          for (int kk = 0; kk < kBQ / 16; ++kk) {
+            const uint64_t pd = umma_desc_sw128(aP + kk * 2048, 16384, 1024);
+            const uint64_t dod = umma_desc_sw128(smem_u32(sDO) + kk * 2048, 16384, 1024);
+            umma_bf16(tm_dv, pd, dod, idesc, (i > 0 || kk > 0));
+          }
+#pragma unroll
+          for (int kk = 0; kk < kBQ / 16; ++kk) {
+            const uint64_t dsd = umma_desc_sw128(aDS + kk * 2048, 16384, 1024);
+            const uint64_t qd = umma_desc_sw128(smem_u32(sQ) + kk * 2048, 16384, 1024);
+            umma_bf16(tm_dk, dsd, qd, idesc, (i > 0 || kk > 0));
+          }
+          // dQ_i = dS K : A = dS K-major (M = 128 queries, K = ncols keys), B = K MN-major (N = 64, K = keys)
+          const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
+          for (int kk = 0; kk < ncols / 16; ++kk) {
+            const uint64_t dsd = umma_desc_sw128(aDS + kk * 32, 16, 1024);
+            const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
+            umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
+          }
+          umma_commit(bar_dq);
         }
-        // dQ_i = dS K : A = dS K-major (M = 128 queries, K = ncols keys), B = K MN-major (N = 64, K = keys)
-        const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
-        for (int kk = 0; kk < ncols / 16; ++kk) {
-          const uint64_t dsd = umma_desc_sw128(aDS + kk * 32, 16, 1024);
-          const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
-          umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
+        __syncwarp();
+        mbar_wait(bar_dq, ph);   // every smem operand of this query tile (and, on the last one, of the item) is free
+        if (elect_one()) {
+          if (i + 1 < nq) {
+            mbar_expect_tx(bar_q, 2 * 16384);
+            tma_load_3d(sQ, &tmap_q, bar_q, h * kDH, (i + 1) * kBQ, b);
+            tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, (i + 1) * kBQ, b);
+          } else if (w + (int)gridDim.x < total) {
+            load_item(w + gridDim.x);
+          }
         }
-        umma_commit(bar_dq);
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(bar_dq, ph);
-      if (i + 1 < nq && elect_one()) {
-        mbar_expect_tx(bar_q, 2 * 16384);
-        tma_load_3d(sQ, &tmap_q, bar_q, h * kDH, (i + 1) * kBQ, b);
-        tma_load_3d(sDO, &tmap_do, bar_q, h * kDH, (i + 1) * kBQ, b);
-      }
-      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- compute warps
@@ -675,98 +694,118 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
     const float sl2 = scale * kLog2e;
     const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
-    const bool tail_block = nvalid_kv < kKB;
-    for (int i = 0; i < nq; ++i) {
-      const uint32_t ph = i & 1;
-      const int q = i * kBQ + r;
-      const bool q_ok = q < N;
-      const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);
-      // rows beyond the sequence get lse = +inf so that exp2(s - lse) = 0 without a select
-      float lse2 = INFINITY, dlt = 0.0f;
-      if (q_ok) {
-        lse2 = lse[((size_t)b * H + h) * N + q] * kLog2e;
-        dlt = delta[((size_t)b * H + h) * N + q];
+    uint32_t qn = 0;
+    // per-row statistics of the NEXT query tile are requested while this one waits for its MMAs
+    // (rows beyond the sequence get lse = +inf so that exp2(s - lse) = 0 without a select)
+    float lse_n = INFINITY, dlt_n = 0.0f;
+    auto fetch_stats = [&](int w_, int i_) {
+      lse_n = INFINITY; dlt_n = 0.0f;
+      const int q_ = i_ * kBQ + r;
+      if (w_ < total && q_ < N) {
+        const size_t o = (size_t)(w_ / nkb) * N + q_;   // (b * H + h) * N + q
+        lse_n = lse[o];
+        dlt_n = delta[o];
       }
-      mbar_wait(bar_s, ph);
-      tc_fence_after();
+    };
+    fetch_stats(blockIdx.x, 0);
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int kb = w % nkb, bh = w / nkb;
+      const int h = bh % H, b = bh / H;
+      const int kv0 = kb * kKB;
+      const int nvalid_kv = min(kKB, N - kv0);
+      const int ncols = (nvalid_kv + 15) & ~15;
+      const bool tail_block = nvalid_kv < kKB;
+      for (int i = 0; i < nq; ++i, ++qn) {
+        const uint32_t ph = qn & 1;
+        const int q = i * kBQ + r;
+        const bool q_ok = q < N;
+        const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);
+        const float lse2 = lse_n * kLog2e, dlt = dlt_n;
+        mbar_wait(bar_s, ph);
+        tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 32 + cc * 16;          // key column of this 16-wide chunk
-        uint32_t pk[8], dsk[8];
-        if (c < ncols) {
-          uint32_t sv[16], dv[16];
-          tmem_ld16(tm_s + lane_off + c, sv);
-          tmem_ld16(tm_dp + lane_off + c, dv);
-          tmem_ld_wait();
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 32 + cc * 16;          // key column of this 16-wide chunk
+          uint32_t pk[8], dsk[8];
+          if (c < ncols) {
+            uint32_t sv[16], dv[16];
+            tmem_ld16(tm_s + lane_off + c, sv);
+            tmem_ld16(tm_dp + lane_off + c, dv);
+            tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 16; k += 2) {
-            bool keep[2] = {true, true};
-            if (drop.thresh != 0u)
-              drop_keep2(2u * (drow + (uint32_t)((kv0 + c + k) >> 1)), dseed, drop.thresh, keep[0], keep[1]);
-            float pdv[2], dsv[2];
+            for (int k = 0; k < 16; k += 2) {
+              bool keep[2] = {true, true};
+              if (drop.thresh != 0u)
+                drop_keep2(2u * (drow + (uint32_t)((kv0 + c + k) >> 1)), dseed, drop.thresh, keep[0], keep[1]);
+              float pdv[2], dsv[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              float pv = ex2_approx(__uint_as_float(sv[k + u]) * sl2 - lse2);
-              if (tail_block) pv = (c + k + u < nvalid_kv) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
-              // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
-              const float mk = keep[u] ? dscale : 0.0f;
-              pdv[u] = pv * mk;
-              dsv[u] = (pv * scale) * (__uint_as_float(dv[k + u]) * mk - dlt);
+              for (int u = 0; u < 2; ++u) {
+                float pv = ex2_approx(__uint_as_float(sv[k + u]) * sl2 - lse2);
+                if (tail_block) pv = (c + k + u < nvalid_kv) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
+                // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
+                const float mk = keep[u] ? dscale : 0.0f;
+                pdv[u] = pv * mk;
+                dsv[u] = (pv * scale) * (__uint_as_float(dv[k + u]) * mk - dlt);
+              }
+              pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
+              dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
             }
-            pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
-            dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { pk[k] = 0u; dsk[k] = 0u; }
           }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { pk[k] = 0u; dsk[k] = 0u; }
+          const uint32_t slot = uint32_t(c >> 3);     // 16-byte slot inside the 128-byte (64-key) row
+          *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot)) = make_uint4(dsk[0], dsk[1], dsk[2], dsk[3]);
+          *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot + 1)) = make_uint4(dsk[4], dsk[5], dsk[6], dsk[7]);
         }
-        const uint32_t slot = uint32_t(c >> 3);     // 16-byte slot inside the 128-byte (64-key) row
-        *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot)) = make_uint4(dsk[0], dsk[1], dsk[2], dsk[3]);
-        *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot + 1)) = make_uint4(dsk[4], dsk[5], dsk[6], dsk[7]);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(bar_pds);
-      mbar_wait(bar_dq, ph);
-      tc_fence_after();
-      // dQ partial of this key block: this thread owns head dims [32*half, +32) of query row q
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+        if (i + 1 < nq) fetch_stats(w, i + 1);
+        else fetch_stats(w + gridDim.x, 0);
+        mbar_wait(bar_dq, ph);
+        tc_fence_after();
+        // dQ partial of this key block: this thread owns head dims [32*half, +32) of query row q
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[16];
+          tmem_ld16(tm_dq + lane_off + half * 32 + cc * 16, v);
+          tmem_ld_wait();
+          if (q_ok) {
+            float* dst = dq_accum + ((size_t)b * N + q) * D + h * kDH + half * 32 + cc * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k),
+                           "f"(__uint_as_float(v[4 * k])), "f"(__uint_as_float(v[4 * k + 1])),
+                           "f"(__uint_as_float(v[4 * k + 2])), "f"(__uint_as_float(v[4 * k + 3]))
+                           : "memory");
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_dqr);
+      }
+      // dK (warps 0-3) and dV (warps 4-7), M = 64 accumulator layout: lanes 0-15 of quadrant `quad` hold keys
+      // 16*quad .. 16*quad+15.  All MMAs of this item completed with its last bar_dq phase.
+      const int kv = kv0 + quad * 16 + lane;
+      const bool kv_ok = lane < 16 && kv < N;
+      const uint32_t src = half == 0 ? tm_dk : tm_dv;
+      __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (half == 0 ? D : 2 * D) + h * kDH;
+#pragma unroll
+      for (int c = 0; c < kDH; c += 16) {
         uint32_t v[16];
-        tmem_ld16(tm_dq + lane_off + half * 32 + cc * 16, v);
+        tmem_ld16(src + lane_off + c, v);
         tmem_ld_wait();
-        if (q_ok) {
-          float* dst = dq_accum + ((size_t)b * N + q) * D + h * kDH + half * 32 + cc * 16;
+        if (kv_ok) {
+          u32x8 o;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k),
-                         "f"(__uint_as_float(v[4 * k])), "f"(__uint_as_float(v[4 * k + 1])),
-                         "f"(__uint_as_float(v[4 * k + 2])), "f"(__uint_as_float(v[4 * k + 3]))
-                         : "memory");
+          for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          st_global_256(dst + c, o);
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_dqr);
-    }
-    // dK (warps 0-3) and dV (warps 4-7), M = 64 accumulator layout: lanes 0-15 of quadrant `quad` hold keys
-    // 16*quad .. 16*quad+15.  All MMAs completed with the last bar_dq phase.
-    const int kv = kv0 + quad * 16 + lane;
-    const bool kv_ok = lane < 16 && kv < N;
-    const uint32_t src = half == 0 ? tm_dk : tm_dv;
-    __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (half == 0 ? D : 2 * D) + h * kDH;
-#pragma unroll
-    for (int c = 0; c < kDH; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(src + lane_off + c, v);
-      tmem_ld_wait();
-      if (kv_ok) {
-        u32x8 o;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o.v[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-        st_global_256(dst + c, o);
-      }
+      mbar_arrive(bar_epi);   // the accumulators may be overwritten by the next item
     }
   }
   tc_fence_before();
@@ -889,7 +928,17 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
                                                                       (const __nv_bfloat16*)dctx, delta, B, N, H);
     VS_CHECK_LAUNCH();
   }
-  dim3 grid((N + kKB - 1) / kKB, H, B);
+  const long long items = (long long)B * H * ((N + kKB - 1) / kKB);
+  VS_CHECK_ARG(items < (1LL << 31), "vs_attention_bwd: too many (batch, head, key block) work items");
+  const int nsm = sm_count();
+  // persistent: two CTAs per SM.  Items are dealt round-robin and the last key block of a sequence is much cheaper
+  // than the others (197 keys = 3 x 64 + 5), so the grid size is made coprime with the number of key blocks: every CTA
+  // then cycles through all key-block indices instead of always drawing the same one.
+  const int nkb = (N + kKB - 1) / kKB;
+  long long g = items < 2LL * nsm ? items : 2LL * nsm;
+  auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+  while (g > 1 && gcd(g, nkb) != 1) --g;
+  const unsigned grid = (unsigned)g;
   attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv,
                                                                   dq_accum, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
