@@ -562,7 +562,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
   uint64_t* bar_dq = bars + 4;
   uint64_t* bar_dqr = bars + 5;
   uint64_t* bar_epi = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* bar_acc = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = H * kDH;
@@ -586,6 +587,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
       mbar_init(bar_dq, 1);
       mbar_init(bar_dqr, 256);
       mbar_init(bar_epi, 256);
+      mbar_init(bar_acc, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -644,8 +646,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
         }
         __syncwarp();
         mbar_wait(bar_pds, ph);
-        if (i == 0 && it > 0) mbar_wait(bar_epi, (it - 1) & 1);   // dK / dV of the previous item have been read out
         tc_fence_after();
+        if (elect_one()) {
+          // dQ_i = dS K first (A = dS K-major: M = 128 queries, K = ncols keys; B = K MN-major: N = 64): the compute
+          // warps read it out and issue their atomics while the 16 accumulator MMAs below are still running
+          const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
+          for (int kk = 0; kk < ncols / 16; ++kk) {
+            const uint64_t dsd = umma_desc_sw128(aDS + kk * 32, 16, 1024);
+            const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
+            umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
+          }
+          umma_commit(bar_dq);
+        }
+        __syncwarp();
+        if (i == 0 && it > 0) {
+          mbar_wait(bar_epi, (it - 1) & 1);   // dK / dV of the previous item have been read out
+          tc_fence_after();
+        }
         if (elect_one()) {
           // dV += P^T dO, dK += dS^T Q : A = P / dS read MN-major (M = 64 keys, K = 128 queries), B MN-major (N = 64)
           const uint32_t idesc = umma_idesc_bf16(kKB, kDH, 1, 1);
@@ -661,17 +678,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
             const uint64_t qd = umma_desc_sw128(smem_u32(sQ) + kk * 2048, 16384, 1024);
             umma_bf16(tm_dk, dsd, qd, idesc, (i > 0 || kk > 0));
           }
-          // dQ_i = dS K : A = dS K-major (M = 128 queries, K = ncols keys), B = K MN-major (N = 64, K = keys)
-          const uint32_t idq = umma_idesc_bf16(kBQ, kDH, 0, 1);
-          for (int kk = 0; kk < ncols / 16; ++kk) {
-            const uint64_t dsd = umma_desc_sw128(aDS + kk * 32, 16, 1024);
-            const uint64_t kd = umma_desc_sw128(smem_u32(sK) + kk * 2048, 16384, 1024);
-            umma_bf16(tm_dq, dsd, kd, idq, kk > 0);
-          }
-          umma_commit(bar_dq);
+          umma_commit(bar_acc);
         }
         __syncwarp();
-        mbar_wait(bar_dq, ph);   // every smem operand of this query tile (and, on the last one, of the item) is free
+        mbar_wait(bar_acc, ph);   // every smem operand of this query tile (and, on the last one, of the item) is free
         if (elect_one()) {
           if (i + 1 < nq) {
             mbar_expect_tx(bar_q, 2 * 16384);
@@ -787,7 +797,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
         mbar_arrive(bar_dqr);
       }
       // dK (warps 0-3) and dV (warps 4-7), M = 64 accumulator layout: lanes 0-15 of quadrant `quad` hold keys
-      // 16*quad .. 16*quad+15.  All MMAs of this item completed with its last bar_dq phase.
+      // 16*quad .. 16*quad+15.  The accumulator MMAs of the item's last query tile complete with bar_acc.
+      mbar_wait(bar_acc, (qn - 1) & 1);
+      tc_fence_after();
       const int kv = kv0 + quad * 16 + lane;
       const bool kv_ok = lane < 16 && kv < N;
       const uint32_t src = half == 0 ? tm_dk : tm_dv;
