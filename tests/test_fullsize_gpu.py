@@ -83,14 +83,17 @@ def test_full_batch_gradient_is_the_mean_of_half_batch_gradients(vitb):
     l_b, g_b = grads(x[32:], y[32:])
     assert abs(l_full - 0.5 * (l_a + l_b)) < 1e-5 * abs(l_full)
     assert math.log(17) - 0.5 < l_full < 20.0        # random weights: no better than the uniform prediction
+    gmax = max(g.abs().max().item() for g in g_full.values())
     worst = 0.0
     for k, g in g_full.items():
         ref = 0.5 * (g_a[k] + g_b[k])
         scale = ref.abs().max().item()
-        if scale < 1e-8:      # key biases: the true gradient is zero
+        if scale < 1e-5 * gmax:   # key biases: softmax is shift-invariant, their true gradient is zero (pure noise)
+            assert k.endswith("attention.key.bias"), k
             continue
         worst = max(worst, (g - ref).abs().max().item() / scale)
-    # bf16 operand rounding of activations / gradients is identical in both computations; the difference comes from
-    # the 1/64 vs 1/32 loss scaling entering the bf16 roundings of the backward tensors and from atomics order
-    assert worst < 2e-2, worst
+    # the 1/64 vs 1/32 loss scaling is a power of two, so every bf16 rounding of the backward tensors is identical in
+    # both computations; what remains is fp32 summation order (split-K, atomics): measured 7.5e-4, the same as the
+    # run-to-run noise of one computation
+    assert worst < 5e-3, worst
     m.zero_grad(set_to_none=True)
