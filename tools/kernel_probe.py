@@ -246,6 +246,15 @@ def probe_head():
         report("conv1x1 bwd dfeat", rel(dfeat, (dl2 @ w2) * (ft.float() > 0)), 1e-2)
         report("conv1x1 bwd dw", rel(dw, dl2.t() @ ft.float()), 1e-4)
         report("conv1x1 bwd db", rel(db, dl2.sum(0)), 1e-4)
+        # other classifier widths (partial / multiple 256-feature chunks) and the binary head
+        for F2, C2 in ((128, 1), (512, 4), (264, 17)):
+            ft2 = bf(torch.relu(torch.randn(Bn * T, F2, device=dev)))
+            w3 = torch.randn(C2, F2, device=dev) * 0.1
+            b3 = torch.randn(C2, device=dev)
+            lg2 = torch.empty(Bn, C2, g, g, device=dev)
+            K.conv1x1_fwd(ft2, w3, b3, lg2, Bn, g, F2, C2)
+            ref2 = (ft2.float() @ w3.t() + b3).view(Bn, T, C2).transpose(1, 2).reshape(Bn, C2, g, g)
+            report(f"conv1x1 fwd F{F2} C{C2}", rel(lg2, ref2), 1e-5)
         # patchify
         img = torch.rand(Bn, 3, 224, 224, device=dev)
         pm = torch.zeros(Bn * (T + 1), 768, device=dev, dtype=torch.bfloat16)

@@ -186,8 +186,15 @@ __global__ void head_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float
 __global__ void __launch_bounds__(256)
 conv1x1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ logits, int B, int T, int F, int C) {
-  extern __shared__ float s_w[];  // [C][F]
-  for (int i = threadIdx.x; i < C * F; i += blockDim.x) s_w[i] = w[i];
+  // weights as [C][F/256][8][32]: lane l holds features 8l .. 8l+7 of a 256-chunk (one 16-byte load), and reads
+  // weight (i, l) at word i*32 + l — conflict-free (the plain [C][F] layout put 8 lanes on every bank: 60 us, ncu r01)
+  extern __shared__ float s_w[];
+  const int Fp = (F + 255) & ~255;   // class stride: whole 256-feature chunks
+  for (int i = threadIdx.x; i < C * F; i += blockDim.x) {
+    const int c = i / F, f = i - c * F;
+    const int chunk = f >> 8, l = (f & 255) >> 3, k = f & 7;
+    s_w[c * Fp + chunk * 256 + k * 32 + l] = w[i];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long npix = (long long)B * T;
@@ -214,7 +221,7 @@ conv1x1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restri
         float s = 0.0f;
         if (f < F) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s += x[i] * s_w[c * F + f + i];
+          for (int i = 0; i < 8; ++i) s += x[i] * s_w[c * Fp + f0 + i * 32 + lane];
         }
         s = warp_sum(s);
         if (lane == 0) {
@@ -234,6 +241,7 @@ conv1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
                    __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db, int B, int T,
                    int F, int C) {
   __shared__ float s_dl[64][kMaxClasses];
+  __shared__ __align__(16) __nv_bfloat16 s_x[64][256];   // feature rows of the current pixel group (F <= 256)
   const int f = threadIdx.x;
   const long long npix = (long long)B * T;
   const long long per = (npix + gridDim.x - 1) / gridDim.x;
@@ -254,12 +262,23 @@ conv1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
       const int b = int(pix / T), t = int(pix - (long long)b * T);
       s_dl[pi][c] = dlogits[((long long)b * C + c) * T + t];
     }
+    // all feature rows of the group in flight at once (16-byte loads) instead of one dependent 2-byte load per pixel
+    // and thread: the kernel was latency-bound (100 us for 6.4 MB, ncu r01)
+    if ((F & 7) == 0) {
+      const int f8 = F >> 3;
+      for (int i = threadIdx.x; i < n * f8; i += blockDim.x) {
+        const int pi = i / f8, q = i - pi * f8;
+        *reinterpret_cast<uint4*>(&s_x[pi][q * 8]) = *reinterpret_cast<const uint4*>(feat + (base + pi) * F + q * 8);
+      }
+    } else {
+      for (int i = threadIdx.x; i < n * F; i += blockDim.x) s_x[i / F][i % F] = feat[(base + i / F) * F + i % F];
+    }
     __syncthreads();
     if (f < C)
       for (int pi = 0; pi < n; ++pi) dbacc += s_dl[pi][f];
     if (f < F) {
       for (int pi = 0; pi < n; ++pi) {
-        const float x = __bfloat162float(feat[(base + pi) * F + f]);
+        const float x = __bfloat162float(s_x[pi][f]);
         float d = 0.0f;
 #pragma unroll
         for (int c = 0; c < kMaxClasses; ++c) {
@@ -454,10 +473,11 @@ extern "C" int vs_head_col2im(const void* dcol, float* dtokens, int32_t B, int32
 extern "C" int vs_conv1x1_fwd(const void* feat, const float* w, const float* b, float* logits, int32_t B, int32_t g,
                               int32_t F, int32_t C, void* stream) {
   VS_CHECK_ARG(feat && w && b && logits && B > 0 && g > 0 && F % 8 == 0 && C > 0, "vs_conv1x1_fwd: bad arguments");
-  VS_CHECK_ARG((size_t)C * F * 4 <= 96 * 1024, "vs_conv1x1_fwd: C*F too large for shared memory");
+  const int Fp = (F + 255) & ~255;
+  VS_CHECK_ARG((size_t)C * Fp * 4 <= 96 * 1024, "vs_conv1x1_fwd: C*F too large for shared memory");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_conv1x1_fwd: no CUDA device");
-  const size_t smem = (size_t)C * F * sizeof(float);
+  const size_t smem = (size_t)C * Fp * sizeof(float);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(conv1x1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
