@@ -392,3 +392,24 @@ def test_graphed_train_step_matches_eager_and_honours_set_lr():
     torch.cuda.synchronize()
     for k, p in b.named_parameters():
         assert torch.equal(p, before[k]), k
+
+
+def test_graphed_inference_equals_eager(tiny):
+    """GraphedInference (one CUDA graph per input shape: the worker path) returns exactly the eager results and sees
+    later weight updates only after a fresh capture — here: same weights, two different inputs."""
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    from visiontransformer_b200.graph import GraphedInference
+    dev = _dev()
+    cfg = O.OracleConfig(**tiny["cfg"])
+    sd = O.seeded_state_dict(cfg, tiny["weights_seed"], head_gain=tiny["head_gain"])
+    m = _build(LightningViTModel, cfg, sd, dev).eval()
+    x1 = O.synthetic_images(2, 224, seed=81).to(dev)
+    x2 = O.synthetic_images(2, 224, seed=82).to(dev)
+    with torch.no_grad():
+        g_logits = GraphedInference(m, x1)
+        g_mask = GraphedInference(m.model.predict_mask, x1)
+        for x in (x1, x2, x1):
+            assert torch.equal(g_logits(x), m(x))
+            assert torch.equal(g_mask(x), m.model.predict_mask(x))
+    with pytest.raises(ValueError):
+        g_logits(x1[:1])
