@@ -24,7 +24,6 @@ namespace vs {
 
 constexpr int kDH = 64;
 constexpr int kBQ = 128;
-constexpr int kBKV = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
