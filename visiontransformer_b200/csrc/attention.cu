@@ -47,22 +47,26 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c32,
 }
 
 // ================================================================================================
-// forward
+// forward, streaming (N > 256: 384x384 and 512x512 inputs, 577 / 1025 tokens)
 // ================================================================================================
-// One CTA per (128-query tile, head, batch); key blocks of 64 with double-buffered K / V stages; three CTAs per SM
-// (64 KB smem, 128 TMEM columns each).  8 softmax warps: warp w owns TMEM lane quadrant (w & 3) — query rows — and
-// half (w >> 2) of the 64 key columns of S and of the 64 head-dim columns of O; the two threads of a row exchange
-// their partial row maxima through smem once per key block.  (The first version — 128-key blocks, 4 softmax warps,
-// 2 CTAs/SM — left each SM with 8 latency-bound warps.)
+// One CTA per (128-query tile, head, batch), key blocks of 64, two CTAs per SM (100 KB smem, 256 TMEM columns each).
+// 8 softmax warps: warp w owns TMEM lane quadrant (w & 3) — query rows — and half (w >> 2) of the 64 key columns of S
+// and of the 64 head-dim columns of O; the two threads of a row exchange their partial row maxima through smem once
+// per key block.
+// Software pipeline (the first streaming version ran S_j -> softmax_j -> P_j V_j -> read O_j strictly in sequence and
+// reached 24 % issue utilisation at N = 1025): S and O are double-buffered in TMEM and P in smem, K / V have three
+// stages.  S_{j+1} is issued before softmax_j finishes, P_j V_j as soon as P_j is in smem, and the softmax warps fold
+// O_{j-1} into their register accumulator (online-softmax rescale) only AFTER handing over P_j — so neither MMA round
+// trip sits on the softmax warps' critical path.
 constexpr int kFKB = 64;
 struct AttnFwdSmem {
   static constexpr int kQ = 0;                 // 128 x 128 B
-  static constexpr int kK = 16384;             // 2 stages x 64 x 128 B
-  static constexpr int kV = 32768;             // 2 stages x 64 x 128 B
-  static constexpr int kP = 49152;             // 128 x 128 B
-  static constexpr int kMax = 65536;           // float [2][2][128] partial row maxima (double-buffered by block)
-  static constexpr int kBar = 65536 + 2048;
-  static constexpr int kTotal = kBar + 128 + 1024;
+  static constexpr int kK = 16384;             // 3 stages x 64 x 128 B
+  static constexpr int kV = 40960;             // 3 stages x 64 x 128 B
+  static constexpr int kP = 65536;             // 2 x (128 x 128 B)
+  static constexpr int kMax = 98304;           // float [2][2][128] partial row maxima (double-buffered by block)
+  static constexpr int kBar = 98304 + 2048;
+  static constexpr int kTotal = kBar + 256 + 1024;
 };
 constexpr int kFwdThreads = 288;
 
@@ -74,12 +78,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::kBar);
-  uint64_t* bar_k = bars + 0;   // [2]
-  uint64_t* bar_v = bars + 2;   // [2]
-  uint64_t* bar_s = bars + 4;
-  uint64_t* bar_p = bars + 5;
-  uint64_t* bar_o = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* bar_k = bars + 0;    // [3]  K stage full (stage 0 also carries Q)
+  uint64_t* bar_v = bars + 3;    // [3]  V stage full
+  uint64_t* bar_s = bars + 6;    // [2]  S buffer written by the MMA
+  uint64_t* bar_p = bars + 8;    // [2]  P buffer written / S buffer consumed by the softmax warps
+  uint64_t* bar_o = bars + 10;   // [2]  O buffer written by the MMA
+  uint64_t* bar_or = bars + 12;  // [2]  O buffer read out by the softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
@@ -90,20 +95,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
       tma_prefetch_desc(&tmap_kv);
-      for (int i = 0; i < 2; ++i) { mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); }
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 256);
-      mbar_init(bar_o, 1);
+      for (int i = 0; i < 3; ++i) { mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&bar_p[i], 256);
+        mbar_init(&bar_o[i], 1);
+        mbar_init(&bar_or[i], 256);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, 256);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+  const uint32_t tmem_base = *tmem_slot;   // S buffers at columns 0 / 64, O buffers at 128 / 192
 
   if (warp == 8) {
     // ---------------------------------------------------------------- control warp (converged; elected lane issues)
@@ -112,26 +119,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint8_t* sV = smem + AttnFwdSmem::kV;
     const uint32_t aP = smem_u32(smem + AttnFwdSmem::kP);
     auto ncols_of = [&](int j) { return min(kFKB, ((N - j * kFKB) + 15) & ~15); };
-    auto issue_s = [&](int j) {   // S_j = Q K_j^T into TMEM cols [0, 64)
+    auto load_k = [&](int j) {
+      mbar_expect_tx(&bar_k[j % 3], 8192);
+      tma_load_3d(sK + (j % 3) * 8192, &tmap_kv, &bar_k[j % 3], D + h * kDH, j * kFKB, b);
+    };
+    auto load_v = [&](int j) {
+      mbar_expect_tx(&bar_v[j % 3], 8192);
+      tma_load_3d(sV + (j % 3) * 8192, &tmap_kv, &bar_v[j % 3], 2 * D + h * kDH, j * kFKB, b);
+    };
+    auto issue_s = [&](int j) {   // S_j = Q K_j^T into S buffer j & 1
       const uint32_t idesc = umma_idesc_bf16(kBQ, ncols_of(j), 0, 0);
       const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t bd = umma_desc_sw128(smem_u32(sK) + (j & 1) * 8192, 16, 1024);
+      const uint64_t bd = umma_desc_sw128(smem_u32(sK) + (j % 3) * 8192, 16, 1024);
 #pragma unroll
-      for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_s, ad + 2 * k, bd + 2 * k, idesc, k > 0);
-      umma_commit(bar_s);
+      for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_base + (j & 1) * 64, ad + 2 * k, bd + 2 * k, idesc, k > 0);
+      umma_commit(&bar_s[j & 1]);
     };
     if (elect_one()) {
       mbar_expect_tx(&bar_k[0], 16384 + 8192);
       tma_load_3d(sQ, &tmap_q, &bar_k[0], h * kDH, q0, b);
       tma_load_3d(sK, &tmap_kv, &bar_k[0], D + h * kDH, 0, b);
-      mbar_expect_tx(&bar_v[0], 8192);
-      tma_load_3d(sV, &tmap_kv, &bar_v[0], 2 * D + h * kDH, 0, b);
-      if (nblk > 1) {
-        mbar_expect_tx(&bar_k[1], 8192);
-        tma_load_3d(sK + 8192, &tmap_kv, &bar_k[1], D + h * kDH, kFKB, b);
-        mbar_expect_tx(&bar_v[1], 8192);
-        tma_load_3d(sV + 8192, &tmap_kv, &bar_v[1], 2 * D + h * kDH, kFKB, b);
-      }
+      load_v(0);
+      for (int j = 1; j < 3 && j < nblk; ++j) { load_k(j); load_v(j); }
     }
     __syncwarp();
     mbar_wait(&bar_k[0], 0);
@@ -139,42 +148,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (elect_one()) issue_s(0);
     __syncwarp();
     for (int j = 0; j < nblk; ++j) {
-      const uint32_t ph = j & 1;
-      const int st = j & 1;
-      const uint32_t kph = (j >> 1) & 1;
-      // S_j complete -> K stage st is free: prefetch K_{j+2}
-      mbar_wait(bar_s, ph);
-      if (j + 2 < nblk && elect_one()) {
-        mbar_expect_tx(&bar_k[st], 8192);
-        tma_load_3d(sK + st * 8192, &tmap_kv, &bar_k[st], D + h * kDH, (j + 2) * kFKB, b);
+      const int sb = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      if (j >= 1) {                       // P_{j-1} V_{j-1} complete -> its V stage is free: V_{j+2}
+        mbar_wait(&bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        if (j + 2 < nblk && elect_one()) load_v(j + 2);
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(bar_p, ph);           // P_j in smem, S_j consumed
-      mbar_wait(&bar_v[st], kph);
+      if (j + 1 < nblk) {                 // S_{j+1}: its buffer was last read by softmax_{j-1}
+        mbar_wait(&bar_k[(j + 1) % 3], ((j + 1) / 3) & 1);
+        if (j >= 1) mbar_wait(&bar_p[(j + 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) issue_s(j + 1);
+        __syncwarp();
+      }
+      mbar_wait(&bar_p[sb], ph);          // P_j in smem, S_j consumed
+      mbar_wait(&bar_v[j % 3], (j / 3) & 1);
+      if (j >= 2) mbar_wait(&bar_or[sb], ((j - 2) >> 1) & 1);   // O_{j-2} has left this O buffer
       tc_fence_after();
       if (elect_one()) {
         const int ncols = ncols_of(j);
         const uint32_t idesc = umma_idesc_bf16(kBQ, kDH, 0, 1);
         for (int kk = 0; kk < ncols / 16; ++kk) {
-          const uint64_t ad = umma_desc_sw128(aP + kk * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(smem_u32(sV) + st * 8192 + kk * 2048, 16384, 1024);
-          umma_bf16(tmem_o, ad, bd, idesc, kk > 0);
+          const uint64_t ad = umma_desc_sw128(aP + sb * 16384 + kk * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(smem_u32(sV) + (j % 3) * 8192 + kk * 2048, 16384, 1024);
+          umma_bf16(tmem_base + 128 + sb * 64, ad, bd, idesc, kk > 0);
         }
-        umma_commit(bar_o);
+        umma_commit(&bar_o[sb]);
       }
       __syncwarp();
-      if (j + 1 < nblk) {             // S_{j+1} right behind PV_j: ready when the softmax warps come back
-        mbar_wait(&bar_k[st ^ 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) issue_s(j + 1);
+      // S_j finished long ago (softmax_j consumed it): its K stage is free: K_{j+3}
+      if (j + 3 < nblk) {
+        mbar_wait(&bar_s[sb], ph);
+        if (elect_one()) load_k(j + 3);
         __syncwarp();
       }
-      mbar_wait(bar_o, ph);           // PV_j complete -> V stage st is free: prefetch V_{j+2}
-      if (j + 2 < nblk && elect_one()) {
-        mbar_expect_tx(&bar_v[st], 8192);
-        tma_load_3d(sV + st * 8192, &tmap_kv, &bar_v[st], 2 * D + h * kDH, (j + 2) * kFKB, b);
-      }
-      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- softmax warps
@@ -188,38 +196,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
     const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);  // pair index base
-    float m_run = -INFINITY, l_run = 0.0f;
+    float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
     float o_acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
+    // o_acc <- o_acc * alpha_{j} + O_j for the block whose P V product sits in O buffer j & 1
+    auto fold_o = [&](int j, float alpha) {
+      mbar_wait(&bar_o[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + 128 + (j & 1) * 64 + lane_off + half * 32 + cc * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[cc * 16 + i] = fmaf(o_acc[cc * 16 + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_or[j & 1]);
+    };
 
     for (int j = 0; j < nblk; ++j) {
-      const uint32_t ph = j & 1;
+      const int sb = j & 1;
       const int kv0 = j * kFKB;
       const int nvalid = min(kFKB, N - kv0);
-      mbar_wait(bar_s, ph);
+      mbar_wait(&bar_s[sb], (j >> 1) & 1);
       tc_fence_after();
       // this thread's 32 key columns of S_j
       float sc[32];
       float m_part = -INFINITY;
+      const int ncols = (nvalid + 15) & ~15;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = half * 32 + cc * 16;
         uint32_t v[16];
-        if (c < ((nvalid + 15) & ~15)) {
-          tmem_ld16(tmem_s + lane_off + c, v);
+        if (c < ncols) {
+          tmem_ld16(tmem_base + sb * 64 + lane_off + c, v);
           tmem_ld_wait();
         }
+        if (nvalid == kFKB) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x = (c + i < nvalid) ? __uint_as_float(v[i]) * sl2 : -INFINITY;
-          sc[cc * 16 + i] = x;
-          m_part = fmaxf(m_part, x);
+          for (int i = 0; i < 16; ++i) {
+            sc[cc * 16 + i] = __uint_as_float(v[i]) * sl2;
+            m_part = fmaxf(m_part, sc[cc * 16 + i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            sc[cc * 16 + i] = (c + i < nvalid) ? __uint_as_float(v[i]) * sl2 : -INFINITY;
+            m_part = fmaxf(m_part, sc[cc * 16 + i]);
+          }
         }
       }
-      s_max[(ph * 2 + half) * 128 + r] = m_part;
+      s_max[(sb * 2 + half) * 128 + r] = m_part;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float m_new = fmaxf(m_run, fmaxf(m_part, s_max[(ph * 2 + (half ^ 1)) * 128 + r]));
+      const float m_new = fmaxf(m_run, fmaxf(m_part, s_max[(sb * 2 + (half ^ 1)) * 128 + r]));
       const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block (m_run = -inf)
       float l_blk = 0.0f;
       uint32_t pk[16];
@@ -232,31 +263,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           drop_keep2(2u * (drow + (uint32_t)((kv0 + half * 32 + i) >> 1)), dseed, drop.thresh, k0, k1);
         pk[i >> 1] = pack_bf16(k0 ? p0 * dscale : 0.0f, k1 ? p1 * dscale : 0.0f);
       }
-      // P_j -> bf16 smem (A operand of P·V): this thread's 32 keys = 4 x 16-byte slots of its 128-byte row
+      // P_j -> bf16 smem (A operand of P·V): this thread's 32 keys = 4 x 16-byte slots of its 128-byte row.  P buffer
+      // sb was last read by P_{j-2} V_{j-2}, whose completion this thread awaited when it folded O_{j-2}.
 #pragma unroll
       for (int sl = 0; sl < 4; ++sl)
-        *reinterpret_cast<uint4*>(sP + sw128_offset(r, half * 4 + sl)) =
+        *reinterpret_cast<uint4*>(sP + sb * 16384 + sw128_offset(r, half * 4 + sl)) =
             make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
-      // O_j: this thread's 32 head-dim columns
-      mbar_wait(bar_o, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[16];
-        tmem_ld16(tmem_o + lane_off + half * 32 + cc * 16, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[cc * 16 + i] = o_acc[cc * 16 + i] * alpha + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
+      mbar_arrive(&bar_p[sb]);
+      // deferred: O_{j-1} (relative to m_{j-1}) joins the accumulator while P_j V_j and S_{j+1} are in flight
+      if (j >= 1) fold_o(j - 1, alpha_prev);
+      alpha_prev = alpha;
     }
+    fold_o(nblk - 1, alpha_prev);
     // total row sum = sum of the two column halves
-    float* s_l = s_max;   // reuse: all reads of s_max completed before the last bar_p / bar_o round trip
+    float* s_l = s_max;   // reuse: every read of s_max precedes the last bar.sync below
     asm volatile("bar.sync 1, 256;" ::: "memory");
     s_l[half * 128 + r] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -276,7 +300,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 128);
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
 
 // ================================================================================================
@@ -884,24 +908,17 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   }
   rc = make_tok_tmap(&tkv, qkv, B, N, 3 * H * kDH, kFKB);
   if (rc) return rc;
-  static int occ = 0;
-  if (occ == 0) {
-    const char* e = getenv("VS_ATTN_FWD_OCC");   // tuning knob: resident CTAs per SM the kernel is compiled for
-    occ = (e && e[0] == '3') ? 3 : 2;
+  static bool attr_stream = false;
+  if (!attr_stream) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        AttnFwdSmem::kTotal));
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       AttnFwdSmem::kTotal));
+    attr_stream = true;
   }
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
-  if (occ == 3)
-    attn_fwd_kernel<3><<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx,
-                                                                                         lse, B, N, H, scale, dc);
-  else
-    attn_fwd_kernel<2><<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx,
-                                                                                         lse, B, N, H, scale, dc);
+  attn_fwd_kernel<2><<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx, lse,
+                                                                                       B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
