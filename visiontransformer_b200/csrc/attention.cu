@@ -195,6 +195,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const float sl2 = scale * kLog2e;
     const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
+    const float lds = log2f(dscale);
     const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);  // pair index base
     float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
     float o_acc[32];
@@ -222,7 +223,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int nvalid = min(kFKB, N - kv0);
       mbar_wait(&bar_s[sb], (j >> 1) & 1);
       tc_fence_after();
-      // this thread's 32 key columns of S_j
+      // this thread's 32 key columns of S_j, kept raw: the softmax scale and the dropout scale are folded into the
+      // exponent (p' = 2^(s*c - m + log2 dscale)), the running maximum is tracked on c*s (c > 0)
       float sc[32];
       float m_part = -INFINITY;
       const int ncols = (nvalid + 15) & ~15;
@@ -237,31 +239,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (nvalid == kFKB) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            sc[cc * 16 + i] = __uint_as_float(v[i]) * sl2;
+            sc[cc * 16 + i] = __uint_as_float(v[i]);
             m_part = fmaxf(m_part, sc[cc * 16 + i]);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            sc[cc * 16 + i] = (c + i < nvalid) ? __uint_as_float(v[i]) * sl2 : -INFINITY;
+            sc[cc * 16 + i] = (c + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
             m_part = fmaxf(m_part, sc[cc * 16 + i]);
           }
         }
       }
-      s_max[(sb * 2 + half) * 128 + r] = m_part;
+      s_max[(sb * 2 + half) * 128 + r] = m_part * sl2;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float m_new = fmaxf(m_run, fmaxf(m_part, s_max[(sb * 2 + (half ^ 1)) * 128 + r]));
+      const float m_new = fmaxf(m_run, fmaxf(m_part * sl2, s_max[(sb * 2 + (half ^ 1)) * 128 + r]));
       const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      const float m_off = m_new - lds;
       float l_blk = 0.0f;
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(sc[i] - m_new), p1 = ex2_approx(sc[i + 1] - m_new);
-        l_blk += p0 + p1;   // the normaliser uses the un-dropped probabilities (dropout acts on softmax output)
+        const float p0 = ex2_approx(fmaf(sc[i], sl2, -m_off)), p1 = ex2_approx(fmaf(sc[i + 1], sl2, -m_off));
+        l_blk += p0 + p1;   // row sum in dropout-scaled units (the normaliser uses the un-dropped probabilities)
         bool k0 = true, k1 = true;
         if (drop.thresh != 0u)   // keys 2k, 2k+1 of a query row share one hash
           drop_keep2(2u * (drow + (uint32_t)((kv0 + half * 32 + i) >> 1)), dseed, drop.thresh, k0, k1);
-        pk[i >> 1] = pack_bf16(k0 ? p0 * dscale : 0.0f, k1 ? p1 * dscale : 0.0f);
+        pk[i >> 1] = pack_bf16(k0 ? p0 : 0.0f, k1 ? p1 : 0.0f);
       }
       // P_j -> bf16 smem (A operand of P·V): this thread's 32 keys = 4 x 16-byte slots of its 128-byte row.  P buffer
       // sb was last read by P_{j-2} V_{j-2}, whose completion this thread awaited when it folded O_{j-2}.
@@ -286,7 +289,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float l_tot = l_run + s_l[(half ^ 1) * 128 + r];
     if (q < N) {
-      const float inv = 1.0f / l_tot;
+      // accumulator and row sum are both in dropout-scaled units: O = acc * dscale / l_tot, l = l_tot / dscale
+      const float inv = dscale / l_tot;
       __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH + half * 32;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -295,7 +299,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int k = 0; k < 8; ++k) o.v[k] = pack_bf16(o_acc[16 * i + 2 * k] * inv, o_acc[16 * i + 2 * k + 1] * inv);
         st_global_256(dst + 16 * i, o);
       }
-      if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * N + q] = (m_run + log2f(l_tot)) * kLn2;
+      if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * N + q] = (m_run + log2f(l_tot) - lds) * kLn2;
     }
   }
   tc_fence_before();
