@@ -166,6 +166,13 @@ int vs_upsample_bilinear_fwd(const float* low, float* full, int32_t B, int32_t C
 int vs_upsample_bilinear_bwd(const float* dfull, float* dlow, int32_t B, int32_t C, int32_t g, int32_t S,
                              void* stream);
 int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, int32_t C, int32_t g, int32_t S, void* stream);
+/* _argmax_stats: the same class map (mask may be NULL) plus exact per-image, per-class pixel counts against int64
+ *   labels [B,S,S]: counts int32 [B, NC, 3] = {intersection, predicted, target}, NC = C (2 for C == 1); overwritten.
+ *   Labels outside [0, NC) are not counted as targets.  Pixel accuracy / IoU / Dice / precision / recall of
+ *   model/PAED/classes.py:430-447,684-689, model/PAED/segmentation.py:38-86 and
+ *   model/CE/datasetTestViTmodel.py:188-217 are functions of these counts (visiontransformer_b200/metrics.py). */
+int vs_upsample_argmax_stats(const float* low, const int64_t* labels, uint8_t* mask, int32_t* counts, int32_t B,
+                             int32_t C, int32_t g, int32_t S, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused upsample + cross-entropy (model/CE/classes.py:276-285: F.interpolate -> nn.CrossEntropyLoss, mean over

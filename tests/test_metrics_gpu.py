@@ -1,0 +1,66 @@
+"""vs_upsample_argmax_stats: exact integer parity of the fused argmax + per-class pixel counts with counts formed from
+the (already parity-tested) class map and the labels, and the wrappers' logged metrics against the reference formulas."""
+import pytest
+import torch
+
+from _metric_refs import (binary_iou_ref, counts_from_maps, dice_score_ref, iou_score_ref, pixel_accuracy_ref)
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("B,C,g,S", [(3, 17, 14, 224), (2, 1, 14, 224), (2, 4, 24, 384), (1, 17, 32, 512), (5, 2, 7, 56)])
+def test_counts_are_exact(B, C, g, S):
+    from visiontransformer_b200 import kernels as K
+    dev = _dev()
+    torch.manual_seed(B * 100 + C)
+    low = torch.randn(B, C, g, g, device=dev) * 3
+    nc = 2 if C == 1 else C
+    labels = torch.randint(0, nc, (B, S, S), device=dev)
+    labels[0, :5, :7] = -100                                  # ignore_index pixels: predicted, never a target
+    mask = torch.empty(B, S, S, device=dev, dtype=torch.uint8)
+    counts = K.upsample_argmax_stats(low, labels, S, mask)
+    want_mask = K.upsample_argmax(low, torch.empty_like(mask))
+    assert torch.equal(mask, want_mask)
+    ref = counts_from_maps(want_mask.long().cpu(), labels.cpu(), nc)
+    assert torch.equal(counts.cpu(), ref)
+    assert int(counts[..., 1].sum()) == B * S * S             # every pixel is predicted exactly once
+    no_mask = K.upsample_argmax_stats(low, labels, S)          # mask output is optional
+    assert torch.equal(no_mask, counts)
+
+
+def test_wrapper_metrics_follow_the_reference_formulas():
+    from oracle import vitseg_oracle as O
+    from visiontransformer_b200 import metrics as M
+    from visiontransformer_b200.paed.classes import LightningViTModel, PAEDTrainer
+    dev = _dev()
+    torch.manual_seed(5)
+    x = torch.rand(2, 3, 224, 224, device=dev)
+    y = torch.randint(0, 17, (2, 256, 256), device=dev)
+    m = LightningViTModel(17, 16, 128, 1, 2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0).to(dev).train()
+    with torch.no_grad():
+        m.model.seg_head[2].weight.mul_(20.0)
+    loss, iou = m._step((x, y))
+    with torch.no_grad():
+        pred = m.model.predict_mask(x).long().cpu()
+        tgt = m._resize_target(y, size=(224, 224)).cpu()
+    assert abs(iou.item() - iou_score_ref(pred, tgt, 17).item()) < 1e-6
+    masks, se, si = [t.to(dev) for t in O.synthetic_binary_targets(2, 224, seed=3)]
+    t = PAEDTrainer(1, 16, 128, 1, 2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0).to(dev).train()
+    _, acc, biou, dice, prec, rec = t._forward_step((x, masks, se, si), 0)
+    with torch.no_grad():
+        bp = t.model.predict_mask(x).int().cpu()
+        mk = masks.int().cpu()
+    assert abs(acc.item() - pixel_accuracy_ref(mk, bp).item()) < 1e-6
+    assert abs(biou.item() - binary_iou_ref(mk, bp).item()) < 1e-6
+    assert abs(dice.item() - dice_score_ref(mk, bp).item()) < 1e-6
+    tp = (bp & mk).sum().float()
+    assert abs(prec.item() - (tp / bp.sum().clamp_min(1)).item()) < 1e-6
+    assert abs(rec.item() - (tp / mk.sum().clamp_min(1)).item()) < 1e-6
+    c = M.segmentation_counts(t.model.forward_lowres(x).detach(), masks.long(), 224)
+    assert torch.equal(M.all_reduce_sum_counts(c)[0], c.sum(0).to(torch.int64))

@@ -58,6 +58,7 @@ _SIGS = {
     "vs_upsample_bilinear_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_upsample_bilinear_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_upsample_argmax": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "vs_upsample_argmax_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_upsample_ce": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_paed_binary_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_paed_binary_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -152,6 +152,78 @@ upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused upsample + argmax + segmentation statistics: the predicted class map AND, per image and
+// class, the exact pixel counts  counts[b][c] = {intersection, predicted, target}  from which pixel accuracy, IoU, Dice,
+// precision and recall follow (model/PAED/classes.py:430-447,684-689; model/PAED/segmentation.py:38-86;
+// model/CE/datasetTestViTmodel.py:188-217) — the reference recomputes them with ~100 eager passes per step.
+// Same prediction rule as upsample_argmax_kernel (C == 1: class 1 iff logit > 0, two classes counted).
+// Counting: per-warp shared histograms; the lanes of a warp that hit the same counter are merged with
+// __match_any_sync so one lane adds the population count.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatMaxClasses = 32;
+__device__ __forceinline__ void warp_hist_add(int* hist, int key, bool valid) {
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const unsigned peers = __match_any_sync(act, key);
+    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) hist[key] += __popc(peers);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256)
+upsample_argmax_stats_kernel(const float* __restrict__ low, const long long* __restrict__ labels,
+                             uint8_t* __restrict__ mask, int* __restrict__ counts, int C, int g, int S, int chunks) {
+  extern __shared__ float s_low[];  // [C][g*g]
+  __shared__ int s_hist[8][3][kStatMaxClasses];   // per warp: intersection / predicted / target
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int warp = threadIdx.x >> 5;
+  const int NC = C == 1 ? 2 : C;
+  for (int i = threadIdx.x; i < C * g * g; i += blockDim.x) s_low[i] = low[(long long)b * C * g * g + i];
+  for (int i = threadIdx.x; i < 8 * 3 * kStatMaxClasses; i += blockDim.x) (&s_hist[0][0][0])[i] = 0;
+  __syncthreads();
+  const float scale = (float)g / (float)S;
+  const int rows_per = (S + chunks - 1) / chunks;
+  const int y_begin = chunk * rows_per, y_end = min(S, y_begin + rows_per);
+  const int npix = (y_end - y_begin) * S;
+  for (int base = 0; base < npix; base += blockDim.x) {   // whole warps stay converged for the match / ballot
+    const int idx = base + threadIdx.x;
+    const bool valid = idx < npix;
+    int pred = 0, tgt = -1;
+    if (valid) {
+      const int y = y_begin + idx / S, x = idx % S;
+      int y0, y1, x0, x1;
+      float ly0, ly1, lx0, lx1;
+      bil_coord(y, scale, g, y0, y1, ly0, ly1);
+      bil_coord(x, scale, g, x0, x1, lx0, lx1);
+      if (C == 1) {
+        pred = bil_sample(s_low, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1) > 0.0f ? 1 : 0;
+      } else {
+        float best = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+          const float v = bil_sample(s_low + c * g * g, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+          if (v > best) { best = v; pred = c; }
+        }
+      }
+      const long long o = ((long long)b * S + y) * S + x;
+      if (mask != nullptr) mask[o] = (uint8_t)pred;
+      const long long t = labels[o];
+      tgt = (t >= 0 && t < NC) ? (int)t : -1;   // ignore_index / out-of-range targets are not counted
+    }
+    warp_hist_add(s_hist[warp][1], pred, valid);
+    warp_hist_add(s_hist[warp][2], tgt, valid && tgt >= 0);
+    warp_hist_add(s_hist[warp][0], pred, valid && tgt == pred);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * NC; i += blockDim.x) {
+    const int k = i / NC, c = i - k * NC;
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_hist[w][k][c];
+    if (t != 0) atomicAdd(&counts[((long long)b * NC + c) * 3 + k], t);
+  }
+}
+
 // ================================================================================================
 // fused upsample + cross-entropy (+ gradient onto the low-res grid)
 // one warp per (image, region); lane = column within the region, rows strided; 2*C accumulators per lane
@@ -711,6 +783,30 @@ extern "C" int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, in
   int chunks = 1;
   while ((long long)B * chunks < (long long)sm_count() * 4 && chunks < S / 8) chunks *= 2;
   upsample_argmax_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(low, mask, C, g, S, chunks);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_upsample_argmax_stats(const float* low, const int64_t* labels, uint8_t* mask, int32_t* counts,
+                                        int32_t B, int32_t C, int32_t g, int32_t S, void* stream) {
+  VS_CHECK_ARG(low && labels && counts, "vs_upsample_argmax_stats: null pointer");
+  if (int rc = check_grid("vs_upsample_argmax_stats", B, C, g, S)) return rc;
+  VS_CHECK_ARG(C <= kStatMaxClasses, "vs_upsample_argmax_stats: C must be <= %d", kStatMaxClasses);
+  const size_t smem = (size_t)C * g * g * sizeof(float);
+  VS_CHECK_ARG(smem <= 190 * 1024, "vs_upsample_argmax_stats: C*g*g too large");
+  static size_t smem_set = 0;
+  if (smem > 40 * 1024 && smem > smem_set) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(upsample_argmax_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    smem_set = smem;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int NC = C == 1 ? 2 : C;
+  VS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * NC * 3 * sizeof(int32_t), st));
+  int chunks = 1;
+  while ((long long)B * chunks < (long long)sm_count() * 4 && chunks < S / 8) chunks *= 2;
+  upsample_argmax_stats_kernel<<<B * chunks, 256, smem, st>>>(low, (const long long*)labels, mask, counts, C, g, S,
+                                                              chunks);
   VS_CHECK_LAUNCH();
   return 0;
 }

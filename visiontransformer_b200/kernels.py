@@ -245,6 +245,22 @@ def upsample_argmax(low, mask):
     return mask
 
 
+def upsample_argmax_stats(low, labels, size, mask=None):
+    """-> int32 counts [B, NC, 3] = {intersection, predicted, target} per image and class (NC = C, or 2 for C == 1);
+    optionally also writes the uint8 class map."""
+    require_cuda(low, "upsample_argmax_stats")
+    B, Cn, g, _ = low.shape
+    assert low.is_contiguous() and labels.dtype == torch.int64 and labels.is_contiguous()
+    assert tuple(labels.shape) == (B, size, size), f"labels must be [B,{size},{size}], got {tuple(labels.shape)}"
+    if mask is not None:
+        assert mask.dtype == torch.uint8 and mask.is_contiguous() and tuple(mask.shape) == (B, size, size)
+    counts = torch.empty(B, 2 if Cn == 1 else Cn, 3, device=low.device, dtype=torch.int32)
+    _count(1)
+    check(_lib.load().vs_upsample_argmax_stats(ptr(low), ptr(labels), ptr(mask), ptr(counts), B, Cn, g, size,
+                                               stream()), "vs_upsample_argmax_stats")
+    return counts
+
+
 def upsample_ce(low, labels, loss_sum, dlow):
     require_cuda(low, "upsample_ce")
     B, Cn, g, _ = low.shape

@@ -8,6 +8,7 @@ from torch.optim import AdamW
 from torch.optim.lr_scheduler import ReduceLROnPlateau
 
 from .. import kernels as K
+from .. import metrics
 from .._lightning import LightningModule
 from ..losses import paed_binary_loss, paed_multiclass_soft_fused
 from ..model import ViTSegmentationModel
@@ -53,9 +54,8 @@ class LightningViTModel(LightningModule):
         y = self._resize_target(y, size=(S, S)).long()
         low = self.model.forward_lowres(x)
         loss = paed_multiclass_soft_fused(low, y, S)
-        with torch.no_grad():
-            preds = K.upsample_argmax(low.detach(), torch.empty(x.shape[0], S, S, device=x.device, dtype=torch.uint8))
-            iou = self.iou_score(preds.long(), y, self.num_classes)
+        with torch.no_grad():   # one fused pass: argmax of the upsampled logits + per-image / per-class pixel counts
+            iou = metrics.iou_score(metrics.segmentation_counts(low, y, S))
         return loss, iou
 
     def training_step(self, batch, batch_idx):
@@ -111,16 +111,12 @@ class PAEDTrainer(LightningModule):
         low = self.model.forward_lowres(images)
         loss = paed_binary_loss(low, masks.float(), sdf_ext, sdf_int, S, group=self.dp_group,
                                 world_size=self.dp_world_size)
-        with torch.no_grad():
-            bin_preds = K.upsample_argmax(low.detach(), torch.empty(images.shape[0], S, S, device=images.device,
-                                                                    dtype=torch.uint8)).int()
-            m = masks.int()
-            acc = segmentation.pixel_accuracy(m, bin_preds)
-            iou = segmentation.intersection_over_union(m, bin_preds)
-            dice = segmentation.dice_score(m, bin_preds)
-            tp = (bin_preds & m).sum().float()
-            prec = tp / bin_preds.sum().float().clamp_min(1.0)
-            rec = tp / m.sum().float().clamp_min(1.0)
+        with torch.no_grad():   # logging metrics from one fused argmax + statistics pass (metrics.py)
+            counts = metrics.segmentation_counts(low, masks, S)
+            acc = metrics.pixel_accuracy(counts)
+            iou = metrics.intersection_over_union(counts)
+            dice = metrics.dice_score(counts)
+            prec, rec = metrics.binary_precision_recall(counts)
         self.log_dict({"train_loss": loss, "train_acc": acc, "train_IoU": iou, "train_dice": dice,
                        "train_precision": prec, "train_recall": rec}, on_epoch=True)
         return loss, acc, iou, dice, prec, rec
