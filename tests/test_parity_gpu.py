@@ -413,3 +413,35 @@ def test_graphed_inference_equals_eager(tiny):
             assert torch.equal(g_mask(x), m.model.predict_mask(x))
     with pytest.raises(ValueError):
         g_logits(x1[:1])
+
+
+def test_patch4_variant_forward_and_training_step_vs_oracle():
+    """P4 variant (3137 tokens, 56x56 grid; IDs 2/5/8 of the reference sweep, datasetTestViTmodel.py:97-107): logits,
+    CE loss and head gradients against the fp32 oracle.  Exercises the K = N = 48 patch-embedding GEMMs, the streaming
+    attention kernels at N = 3137 and the row-range staging of the upsample kernels (C * g * g floats = 213 KB)."""
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    dev = _dev()
+    cfg = O.OracleConfig(num_classes=17, patch_size=4, hidden_size=128, num_hidden_layers=1, num_attention_heads=2)
+    sd = O.seeded_state_dict(cfg, 91, head_gain=4.0)
+    m = _build(LightningViTModel, cfg, sd, dev)
+    x = O.synthetic_images(1, 224, seed=92)
+    y = O.synthetic_labels(1, 17, seed=93)
+    m.eval()
+    with torch.no_grad():
+        full = m(x.to(dev))
+        mask = m.model.predict_mask(x.to(dev))
+        ref = O.forward(sd, x, cfg)
+    assert _relmax(full, ref) < LOGIT_TOL
+    assert (mask.long().cpu() == full.cpu().argmax(1)).float().mean().item() > 0.9999
+    m.train()
+    loss = m.training_step((x.to(dev), y.to(dev)), 0)
+    loss.backward()
+    keys = ("seg_head.2.weight", "seg_head.0.bias", "backbone.embeddings.patch_embeddings.projection.weight")
+    sdr = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    ref_loss = O.ce_loss(O.forward(sdr, x, cfg), O.resize_target(y, 224))     # model/CE/classes.py:276-285
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 2e-3 * abs(ref_loss.item())
+    for key in keys:
+        g = dict(m.model.named_parameters())[key].grad.cpu()
+        r = sdr[key].grad
+        assert (g - r).abs().max().item() <= 3e-2 * r.abs().max().item() + 1e-7, key

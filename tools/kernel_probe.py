@@ -102,6 +102,10 @@ def probe_gemm():
     case(1000, 256, 6912, False, True, aux_mode=2)
     case(128, 256, 64, True, False, f32=True)
     case(128, 256, 64, True, True, f32=True)
+    # patch-4 embedding shapes: K = N = 3 * 4 * 4 = 48 (partial k-block, 16-column tail)
+    case(6274, 128, 48, False, False, bias=True, res=True, f32=True)
+    case(128, 48, 6274, True, True, f32=True, acc=True)
+    case(300, 48, 128, False, True)
     case(768, 3072, 1000, True, True, f32=True, acc=True)
     case(768, 768, 12608, True, True, f32=True, acc=True)
     case(2304, 768, 4000, True, True, f32=True, acc=True, split_k=3)

@@ -570,7 +570,7 @@ using namespace vs;
 extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   VS_CHECK_ARG(d != nullptr, "vs_gemm_bf16: null descriptor");
   VS_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "vs_gemm_bf16: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
-  VS_CHECK_ARG(d->N % 32 == 0, "vs_gemm_bf16: N=%d must be a multiple of 32", d->N);
+  VS_CHECK_ARG(d->N % 16 == 0, "vs_gemm_bf16: N=%d must be a multiple of 16 (epilogue chunks)", d->N);
   VS_CHECK_ARG(d->A && d->B && d->out, "vs_gemm_bf16: null operand");
   VS_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0, "vs_gemm_bf16: lda/ldb must be multiples of 8 elements");
   VS_CHECK_ARG(((uintptr_t)d->A % 16 == 0) && ((uintptr_t)d->B % 16 == 0) && ((uintptr_t)d->out % 16 == 0),

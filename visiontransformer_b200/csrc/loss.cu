@@ -115,16 +115,45 @@ upsample_bwd_kernel(const float* __restrict__ dfull, float* __restrict__ dlow, l
   }
 }
 
+// The "image in shared memory" kernels stage only the low-resolution rows their output-row chunk interpolates from
+// (all of them when one block handles the whole image): C * g * g floats no longer bound the grid size, so patch-4
+// models (g = 56, C = 17: 213 KB for whole planes) run.  Returns the plane stride (rows * g) and sets `base` so that
+// base + c * stride indexes like a full plane: base[c * stride + y * g + x] for staged rows y.
+__device__ __forceinline__ int low_rows_needed(int y_begin, int y_end, float scale, int g, int& r0) {
+  int a0, a1, b0, b1;
+  float t0, t1;
+  bil_coord(y_begin, scale, g, a0, a1, t0, t1);
+  bil_coord(y_end - 1, scale, g, b0, b1, t0, t1);
+  r0 = a0;
+  return b1 - a0 + 1;
+}
+__device__ __forceinline__ const float* stage_low_rows(const float* __restrict__ low_b, float* s_low, int C, int g,
+                                                       int r0, int nrows) {
+  const int per = nrows * g;
+  for (int i = threadIdx.x; i < C * per; i += blockDim.x) {
+    const int c = i / per, o = i - c * per;
+    s_low[i] = low_b[(long long)c * g * g + r0 * g + o];
+  }
+  return s_low - r0 * g;
+}
+static int low_rows_bound(int rows_per, int g, int S) {   // host: upper bound of low_rows_needed for a chunk
+  const int n = (rows_per * g + S - 1) / S + 2;
+  return n < g ? n : g;
+}
+
 __global__ void __launch_bounds__(256)
 upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask, int C, int g, int S, int chunks) {
-  extern __shared__ float s_low[];  // [C][g*g]
+  extern __shared__ float s_low_raw[];  // [C][staged rows][g]
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-  for (int i = threadIdx.x; i < C * g * g; i += blockDim.x) s_low[i] = low[(long long)b * C * g * g + i];
-  __syncthreads();
   const float scale = (float)g / (float)S;
   const int S4 = S / 4;
   const int rows_per = (S + chunks - 1) / chunks;
   const int y_begin = chunk * rows_per, y_end = min(S, y_begin + rows_per);
+  if (y_begin >= y_end) return;
+  int r0;
+  const int pstride = low_rows_needed(y_begin, y_end, scale, g, r0) * g;
+  const float* s_low = stage_low_rows(low + (long long)b * C * g * g, s_low_raw, C, g, r0, pstride / g);
+  __syncthreads();
   for (int idx = y_begin * S4 + threadIdx.x; idx < y_end * S4; idx += blockDim.x) {
     const int y = idx / S4, x4 = (idx - y * S4) * 4;
     int y0, y1;
@@ -142,7 +171,7 @@ upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask
         float best = -INFINITY;
         int bi = 0;
         for (int c = 0; c < C; ++c) {
-          const float v = bil_sample(s_low + c * g * g, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+          const float v = bil_sample(s_low + c * pstride, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
           if (v > best) { best = v; bi = c; }
         }
         res[k] = (uint8_t)bi;
@@ -174,17 +203,20 @@ __device__ __forceinline__ void warp_hist_add(int* hist, int key, bool valid) {
 __global__ void __launch_bounds__(256)
 upsample_argmax_stats_kernel(const float* __restrict__ low, const long long* __restrict__ labels,
                              uint8_t* __restrict__ mask, int* __restrict__ counts, int C, int g, int S, int chunks) {
-  extern __shared__ float s_low[];  // [C][g*g]
+  extern __shared__ float s_low_raw[];  // [C][staged rows][g]
   __shared__ int s_hist[8][3][kStatMaxClasses];   // per warp: intersection / predicted / target
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   const int warp = threadIdx.x >> 5;
   const int NC = C == 1 ? 2 : C;
-  for (int i = threadIdx.x; i < C * g * g; i += blockDim.x) s_low[i] = low[(long long)b * C * g * g + i];
-  for (int i = threadIdx.x; i < 8 * 3 * kStatMaxClasses; i += blockDim.x) (&s_hist[0][0][0])[i] = 0;
-  __syncthreads();
   const float scale = (float)g / (float)S;
   const int rows_per = (S + chunks - 1) / chunks;
   const int y_begin = chunk * rows_per, y_end = min(S, y_begin + rows_per);
+  if (y_begin >= y_end) return;
+  int r0;
+  const int pstride = low_rows_needed(y_begin, y_end, scale, g, r0) * g;
+  const float* s_low = stage_low_rows(low + (long long)b * C * g * g, s_low_raw, C, g, r0, pstride / g);
+  for (int i = threadIdx.x; i < 8 * 3 * kStatMaxClasses; i += blockDim.x) (&s_hist[0][0][0])[i] = 0;
+  __syncthreads();
   const int npix = (y_end - y_begin) * S;
   for (int base = 0; base < npix; base += blockDim.x) {   // whole warps stay converged for the match / ballot
     const int idx = base + threadIdx.x;
@@ -201,7 +233,7 @@ upsample_argmax_stats_kernel(const float* __restrict__ low, const long long* __r
       } else {
         float best = -INFINITY;
         for (int c = 0; c < C; ++c) {
-          const float v = bil_sample(s_low + c * g * g, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+          const float v = bil_sample(s_low + c * pstride, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
           if (v > best) { best = v; pred = c; }
         }
       }
@@ -335,7 +367,8 @@ upsample_ce_kernel(const float* __restrict__ low, const long long* __restrict__ 
 // stats[b*8 + {0..6}] = {sum bce, sum p*t, sum p, sum t, sum sdf_int*p, sum sdf_ext*edge, -}; keys[b] = packed
 // (edge bits << 32 | ~pixel index) maximum, i.e. the per-image max edge and its FIRST arg-max (torch.max semantics).
 // ================================================================================================
-constexpr int kMaxP = 32;
+constexpr int kMaxP = 32;   // largest patch size (pixels per grid cell)
+constexpr int kMaxG = 64;   // largest grid side the PAED-binary kernels stage (patch 4 at 224: 56)
 
 __device__ __forceinline__ float sigmoid_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
 
@@ -369,7 +402,7 @@ __global__ void __launch_bounds__(256)
 paed_binary_stats_kernel(const float* __restrict__ low, const float* __restrict__ mask, const float* __restrict__ sdf_ext,
                          const float* __restrict__ sdf_int, float* __restrict__ stats,
                          unsigned long long* __restrict__ keys, int B, int g, int S) {
-  __shared__ float s_low[kMaxP * kMaxP];
+  __shared__ float s_low[kMaxG * kMaxG];
   __shared__ float s_p[(kMaxP + 2) * (kMaxP + 2)];
   __shared__ float s_red[8][6];
   __shared__ unsigned long long s_key[8];
@@ -432,7 +465,7 @@ __global__ void __launch_bounds__(256)
 paed_binary_bwd_kernel(const float* __restrict__ low, const float* __restrict__ mask, const float* __restrict__ sdf_ext,
                        const float* __restrict__ sdf_int, const float* __restrict__ coef,
                        const unsigned long long* __restrict__ keys, float* __restrict__ dlow, int B, int g, int S) {
-  __shared__ float s_low[kMaxP * kMaxP];
+  __shared__ float s_low[kMaxG * kMaxG];
   __shared__ float s_p[(kMaxP + 4) * (kMaxP + 4)];
   __shared__ float s_gx[(kMaxP + 2) * (kMaxP + 2)];
   __shared__ float s_gy[(kMaxP + 2) * (kMaxP + 2)];
@@ -518,14 +551,17 @@ __global__ void __launch_bounds__(256)
 pm_pixel_kernel(const float* __restrict__ low, const long long* __restrict__ labels, const float* __restrict__ tin,
                 const float* __restrict__ bu, float* __restrict__ out, float* __restrict__ loss_sum, int mode, int C,
                 int g, int S, int chunks) {
-  extern __shared__ float s_low[];
+  extern __shared__ float s_low_raw[];  // [C][staged rows][g]
   __shared__ float s_red[8];
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-  for (int i = threadIdx.x; i < C * g * g; i += blockDim.x) s_low[i] = low[(long long)b * C * g * g + i];
-  __syncthreads();
   const float scale = (float)g / (float)S;
   const int rows_per = (S + chunks - 1) / chunks;
   const int y_begin = chunk * rows_per, y_end = min(S, y_begin + rows_per);
+  if (y_begin >= y_end) return;
+  int r0;
+  const int pstride = low_rows_needed(y_begin, y_end, scale, g, r0) * g;
+  const float* s_low = stage_low_rows(low + (long long)b * C * g * g, s_low_raw, C, g, r0, pstride / g);
+  __syncthreads();
   const long long plane = (long long)S * S;
   float loss = 0.0f;
   for (int idx = y_begin * S + threadIdx.x; idx < y_end * S; idx += blockDim.x) {
@@ -543,7 +579,7 @@ pm_pixel_kernel(const float* __restrict__ low, const long long* __restrict__ lab
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
       if (c < C) {
-        z[c] = bil_sample(s_low + c * g * g, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+        z[c] = bil_sample(s_low + c * pstride, g, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
         m = fmaxf(m, z[c]);
       }
     float s = 0.0f;
@@ -768,20 +804,39 @@ extern "C" int vs_upsample_bilinear_bwd(const float* dfull, float* dlow, int32_t
   return 0;
 }
 
+// chunks (output-row groups per image) and dynamic smem of the image-in-smem kernels: enough blocks to fill the GPU,
+// and more chunks when the staged low-resolution rows would not fit otherwise
+static int plan_image_chunks(const char* who, int B, int C, int g, int S, int max_chunks, int* chunks_out,
+                             size_t* smem_out) {
+  const size_t limit = 160 * 1024;
+  int chunks = 1;
+  while ((long long)B * chunks < (long long)sm_count() * 4 && chunks < max_chunks) chunks *= 2;
+  for (;;) {
+    const int rows_per = (S + chunks - 1) / chunks;
+    const size_t smem = (size_t)C * low_rows_bound(rows_per, g, S) * g * sizeof(float);
+    if (smem <= limit || chunks >= S / 2) {
+      if (smem > limit) { set_error("%s: C=%d, g=%d does not fit shared memory", who, C, g); return -1; }
+      *chunks_out = chunks;
+      *smem_out = smem;
+      return 0;
+    }
+    chunks *= 2;
+  }
+}
+
 extern "C" int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, int32_t C, int32_t g, int32_t S,
                                   void* stream) {
   VS_CHECK_ARG(low && mask, "vs_upsample_argmax: null pointer");
   if (int rc = check_grid("vs_upsample_argmax", B, C, g, S)) return rc;
   VS_CHECK_ARG(C <= 255, "vs_upsample_argmax: C must be <= 255");
-  const size_t smem = (size_t)C * g * g * sizeof(float);
-  VS_CHECK_ARG(smem <= 200 * 1024, "vs_upsample_argmax: C*g*g too large");
+  int chunks;
+  size_t smem;
+  if (int rc = plan_image_chunks("vs_upsample_argmax", B, C, g, S, S / 8, &chunks, &smem)) return rc;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(upsample_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  int chunks = 1;
-  while ((long long)B * chunks < (long long)sm_count() * 4 && chunks < S / 8) chunks *= 2;
   upsample_argmax_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(low, mask, C, g, S, chunks);
   VS_CHECK_LAUNCH();
   return 0;
@@ -792,8 +847,9 @@ extern "C" int vs_upsample_argmax_stats(const float* low, const int64_t* labels,
   VS_CHECK_ARG(low && labels && counts, "vs_upsample_argmax_stats: null pointer");
   if (int rc = check_grid("vs_upsample_argmax_stats", B, C, g, S)) return rc;
   VS_CHECK_ARG(C <= kStatMaxClasses, "vs_upsample_argmax_stats: C must be <= %d", kStatMaxClasses);
-  const size_t smem = (size_t)C * g * g * sizeof(float);
-  VS_CHECK_ARG(smem <= 190 * 1024, "vs_upsample_argmax_stats: C*g*g too large");
+  int chunks;
+  size_t smem;
+  if (int rc = plan_image_chunks("vs_upsample_argmax_stats", B, C, g, S, S / 8, &chunks, &smem)) return rc;
   static size_t smem_set = 0;
   if (smem > 40 * 1024 && smem > smem_set) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(upsample_argmax_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -803,8 +859,6 @@ extern "C" int vs_upsample_argmax_stats(const float* low, const int64_t* labels,
   cudaStream_t st = (cudaStream_t)stream;
   const int NC = C == 1 ? 2 : C;
   VS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * NC * 3 * sizeof(int32_t), st));
-  int chunks = 1;
-  while ((long long)B * chunks < (long long)sm_count() * 4 && chunks < S / 8) chunks *= 2;
   upsample_argmax_stats_kernel<<<B * chunks, 256, smem, st>>>(low, (const long long*)labels, mask, counts, C, g, S,
                                                               chunks);
   VS_CHECK_LAUNCH();
@@ -833,7 +887,7 @@ extern "C" int vs_paed_binary_stats(const float* low, const float* mask, const f
                                     float* stats, uint64_t* keys, int32_t B, int32_t g, int32_t S, void* stream) {
   VS_CHECK_ARG(low && mask && sdf_ext && sdf_int && stats && keys, "vs_paed_binary_stats: null pointer");
   if (int rc = check_grid("vs_paed_binary_stats", B, 1, g, S)) return rc;
-  VS_CHECK_ARG(g <= kMaxP, "vs_paed_binary_stats: g must be <= %d", kMaxP);
+  VS_CHECK_ARG(g <= kMaxG, "vs_paed_binary_stats: g must be <= %d", kMaxG);
   const long long nreg = (long long)B * (g + 1) * (g + 1);
   paed_binary_stats_kernel<<<(unsigned)nreg, 256, 0, (cudaStream_t)stream>>>(low, mask, sdf_ext, sdf_int, stats,
                                                                             (unsigned long long*)keys, B, g, S);
@@ -846,7 +900,7 @@ extern "C" int vs_paed_binary_bwd(const float* low, const float* mask, const flo
                                   void* stream) {
   VS_CHECK_ARG(low && mask && sdf_ext && sdf_int && coef && keys && dlow, "vs_paed_binary_bwd: null pointer");
   if (int rc = check_grid("vs_paed_binary_bwd", B, 1, g, S)) return rc;
-  VS_CHECK_ARG(g <= kMaxP, "vs_paed_binary_bwd: g must be <= %d", kMaxP);
+  VS_CHECK_ARG(g <= kMaxG, "vs_paed_binary_bwd: g must be <= %d", kMaxG);
   const long long nreg = (long long)B * (g + 1) * (g + 1);
   paed_binary_bwd_kernel<<<(unsigned)nreg, 256, 0, (cudaStream_t)stream>>>(low, mask, sdf_ext, sdf_int, coef,
                                                                           (const unsigned long long*)keys, dlow, B, g, S);
@@ -857,15 +911,14 @@ extern "C" int vs_paed_binary_bwd(const float* low, const float* mask, const flo
 template <int CMAX>
 static int paed_multiclass_impl(const float* low, const long long* labels, float* t1, float* t2, float* t3,
                                 float* loss_sum, float* dlow, int B, int C, int g, int S, cudaStream_t st) {
-  const int nsm = sm_count();
-  const size_t smem = (size_t)C * g * g * sizeof(float);
+  int chunks;
+  size_t smem;
+  if (int rc = plan_image_chunks("vs_paed_multiclass", B, C, g, S, S / 4, &chunks, &smem)) return rc;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(pm_pixel_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  int chunks = 1;
-  while ((long long)B * chunks < (long long)nsm * 4 && chunks < S / 4) chunks *= 2;
   const long long planes = (long long)B * C;
   // t1 = onehot - p ; t2 = blur(t1) = t
   pm_pixel_kernel<CMAX><<<B * chunks, 256, smem, st>>>(low, labels, nullptr, nullptr, t1, nullptr, 0, C, g, S, chunks);
