@@ -227,6 +227,18 @@ int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, int32_t row_len, fl
                     const uint32_t* dropout_seed, uint32_t dropout_site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * PAED signed-distance targets on the device: compute_sdf (model/PAED/segmentation.py:6-34) for a batch of masks.
+ *   mask fp32 [B,S,S] (> 0.5 = object) -> sdf_ext = EDT(~mask) / max, sdf_int = EDT(mask) / max, fp32 [B,S,S], each
+ *   divided by its own per-image maximum when that is > 0.  Exact Euclidean distance transform (integer squared
+ *   distances, double-precision root rounded to fp32 as SciPy does); images without any zero element reproduce
+ *   scipy.ndimage.distance_transform_edt's virtual zero at (row -1, col 0).
+ *   workspace: vs_sdf_workspace_bytes(B, S) bytes of device memory, 4-byte aligned, caller-owned.
+ * ------------------------------------------------------------------------------------------------ */
+int64_t vs_sdf_workspace_bytes(int32_t B, int32_t S);
+int vs_sdf_targets(const float* mask, float* sdf_ext, float* sdf_int, void* workspace, int32_t B, int32_t S,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Weight shadows: fp32 master -> bf16 copy (one pass), plus utility conversions.
  *   vs_cast_f32_bf16: n elements.  vs_pack_conv3x3: OIHW fp32 [O,I,3,3] -> bf16 [O, (ky,kx,I)].
  *   vs_unpack_conv3x3_grad: fp32 [O,(ky,kx,I)] -> += OIHW fp32 grad.

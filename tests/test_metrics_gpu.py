@@ -64,3 +64,25 @@ def test_wrapper_metrics_follow_the_reference_formulas():
     assert abs(rec.item() - (tp / mk.sum().clamp_min(1)).item()) < 1e-6
     c = M.segmentation_counts(t.model.forward_lowres(x).detach(), masks.long(), 224)
     assert torch.equal(M.all_reduce_sum_counts(c)[0], c.sum(0).to(torch.int64))
+
+
+@pytest.mark.parametrize("S", [224, 96, 384])
+def test_sdf_targets_are_bit_identical_to_compute_sdf(S):
+    """vs_sdf_targets (exact EDT on the device) against compute_sdf = scipy.ndimage.distance_transform_edt, the
+    reference's own call (model/PAED/segmentation.py:22-32): random discs, a single pixel, an empty and a full mask."""
+    import numpy as np
+    from oracle import vitseg_oracle as O
+    from visiontransformer_b200.paed.segmentation import compute_sdf_batch
+    dev = _dev()
+    masks, se, si = O.synthetic_binary_targets(4, S, seed=S)
+    extra = torch.zeros(4, S, S)
+    extra[0, S // 3, S // 2] = 1.0                      # one object pixel
+    extra[1] = 1.0                                      # full mask: EDT(~mask) = 0, EDT(mask) hits SciPy's virtual zero
+    extra[2, :, : S // 2] = 1.0                         # half plane (whole rows / columns without a zero)
+    # extra[3] stays empty
+    masks = torch.cat([masks, extra])
+    ref = [O.compute_sdf(m.numpy().astype(np.uint8)) for m in masks]
+    ext, inn = compute_sdf_batch(masks.to(dev))
+    for b in range(masks.shape[0]):
+        assert torch.equal(ext[b].cpu(), torch.from_numpy(ref[b][0])), ("ext", b)
+        assert torch.equal(inn[b].cpu(), torch.from_numpy(ref[b][1])), ("int", b)

@@ -42,3 +42,7 @@ def pm():
 
 t("upsample + CE fwd+bwd", ce)
 t("PAED multi-class soft (fused) fwd+bwd", pm)
+
+from visiontransformer_b200.paed.segmentation import compute_sdf_batch  # noqa: E402
+
+t("compute_sdf_batch (exact EDT, B=64, 224x224)", lambda: compute_sdf_batch(masks))

@@ -59,6 +59,8 @@ _SIGS = {
     "vs_upsample_bilinear_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_upsample_argmax": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_upsample_argmax_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "vs_sdf_workspace_bytes": [c_int, c_int],
+    "vs_sdf_targets": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "vs_upsample_ce": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_paed_binary_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_paed_binary_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -92,7 +94,7 @@ def load() -> C.CDLL:
     lib.vs_last_error.argtypes = []
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name.endswith("_bytes") else C.c_int
         fn.argtypes = args
     _lib = lib
     return lib

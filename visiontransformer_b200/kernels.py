@@ -261,6 +261,19 @@ def upsample_argmax_stats(low, labels, size, mask=None):
     return counts
 
 
+def sdf_targets(mask):
+    """mask fp32 [B,S,S] (object > 0.5) -> (sdf_ext, sdf_int) fp32 [B,S,S]: compute_sdf of every image, on the device."""
+    require_cuda(mask, "sdf_targets")
+    assert mask.dtype == F32 and mask.dim() == 3 and mask.shape[1] == mask.shape[2] and mask.is_contiguous()
+    B, S, _ = mask.shape
+    lib = _lib.load()
+    work = torch.empty(int(lib.vs_sdf_workspace_bytes(B, S)), device=mask.device, dtype=torch.uint8)
+    ext, inn = torch.empty_like(mask), torch.empty_like(mask)
+    _count(3)
+    check(lib.vs_sdf_targets(ptr(mask), ptr(ext), ptr(inn), ptr(work), B, S, stream()), "vs_sdf_targets")
+    return ext, inn
+
+
 def upsample_ce(low, labels, loss_sum, dlow):
     require_cuda(low, "upsample_ce")
     B, Cn, g, _ = low.shape

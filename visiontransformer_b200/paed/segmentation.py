@@ -1,5 +1,6 @@
-"""Host-side helpers of model/PAED/segmentation.py: SDF target generation (dataset side, SciPy EDT on the CPU —
-an input producer, not part of the device hot path) and the binary monitoring metrics."""
+"""Helpers of model/PAED/segmentation.py: SDF target generation — compute_sdf as in the reference (dataset side, SciPy
+EDT on the CPU) and compute_sdf_batch, the same transform for a whole batch on the device — and the binary monitoring
+metrics."""
 import numpy as np
 import torch
 
@@ -16,6 +17,15 @@ def compute_sdf(mask: np.ndarray):
     if sdf_int.max() > 0:
         sdf_int /= sdf_int.max()
     return sdf_ext, sdf_int
+
+
+def compute_sdf_batch(masks: torch.Tensor):
+    """Device version of compute_sdf for a batch: masks [B,S,S] or [B,1,S,S] (any dtype, object = non-zero) on a CUDA
+    device -> (sdf_ext, sdf_int) fp32 [B,S,S], bit-identical to compute_sdf per image (vs_sdf_targets: exact EDT)."""
+    from .. import kernels as K
+    if masks.dim() == 4:
+        masks = masks.squeeze(1)
+    return K.sdf_targets((masks != 0).to(torch.float32).contiguous())
 
 
 def pixel_accuracy(gt: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
