@@ -102,7 +102,7 @@ class ClockSampler:
 # reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_reference_step_time(steps: int, warmup: int, batch: int = CPU_SAMPLE_BATCH):
-    """CE training step (fwd + bwd + Adam, fp32, dropout off) of ViT-B/16 on `batch` images — the reference's
+    """CE training step (fwd + bwd + Adam, fp32, dropout 0.1 as the reference's train mode) of ViT-B/16 on `batch` images — the reference's
     createViTmodel.py hot loop restated by oracle/vitseg_oracle.py.  Returns (seconds per step, threads)."""
     from oracle import vitseg_oracle as O
     threads = os.cpu_count() or 1
@@ -117,7 +117,7 @@ def cpu_reference_step_time(steps: int, warmup: int, batch: int = CPU_SAMPLE_BAT
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        loss = O.ce_loss(O.forward(leaves, x, cfg), y)
+        loss = O.ce_loss(O.forward(leaves, x, cfg, dropout=(0.1, 0.1)), y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -142,7 +142,7 @@ def run_reference(args):
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ViT-B/16 CE segmentation training, 224x224, C=17 (BASELINE configs[1] model; CPU sample "
-                               f"batch {CPU_SAMPLE_BATCH})", "dropout": 0.0},
+                               f"batch {CPU_SAMPLE_BATCH})", "dropout": 0.1},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -105,18 +105,23 @@ def seeded_state_dict(cfg: OracleConfig, seed: int, bf16_representable: bool = T
 # ------------------------------------------------------------------------------------------------------------
 # forward
 # ------------------------------------------------------------------------------------------------------------
-def embeddings(sd, x, cfg):
-    """TF:153-167 (conv patch projection, flatten, transpose) + TF:100-128 (CLS, position embeddings)."""
+def _drop(t, p):
+    """nn.Dropout in train mode (TF:126,267,310; SDPA:96 dropout_p); p = 0 is the identity used by every parity test."""
+    return F.dropout(t, p, training=True) if p > 0.0 else t
+
+
+def embeddings(sd, x, cfg, p_hidden=0.0):
+    """TF:153-167 (conv patch projection, flatten, transpose) + TF:100-128 (CLS, position embeddings, dropout)."""
     P = cfg.patch_size
     h = F.conv2d(x, sd["backbone.embeddings.patch_embeddings.projection.weight"],
                  sd["backbone.embeddings.patch_embeddings.projection.bias"], stride=P)
     h = h.flatten(2).transpose(1, 2)
     cls = sd["backbone.embeddings.cls_token"].expand(x.shape[0], -1, -1)
     h = torch.cat((cls, h), dim=1)
-    return h + sd["backbone.embeddings.position_embeddings"]
+    return _drop(h + sd["backbone.embeddings.position_embeddings"], p_hidden)
 
 
-def encoder_layer(sd, h, i, cfg):
+def encoder_layer(sd, h, i, cfg, p_hidden=0.0, p_attn=0.0):
     """TF:328-346 pre-LN block; attention TF:220-251 with SDPA:92-101 (scale = head_dim**-0.5, non-causal);
     MLP TF:290-312 with exact-erf GELU."""
     p = f"backbone.encoder.layer.{i}."
@@ -130,19 +135,21 @@ def encoder_layer(sd, h, i, cfg):
             .view(B, N, H, dh).transpose(1, 2)
 
     q, k, v = proj("query"), proj("key"), proj("value")
-    att = torch.softmax((q @ k.transpose(-1, -2)) * (dh ** -0.5), dim=-1)
+    att = _drop(torch.softmax((q @ k.transpose(-1, -2)) * (dh ** -0.5), dim=-1), p_attn)
     ctx = (att @ v).transpose(1, 2).reshape(B, N, D)
-    h = h + F.linear(ctx, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"])
+    h = h + _drop(F.linear(ctx, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"]),
+                  p_hidden)
     y = F.layer_norm(h, (D,), sd[p + "layernorm_after.weight"], sd[p + "layernorm_after.bias"], cfg.layer_norm_eps)
     y = F.gelu(F.linear(y, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
-    return h + F.linear(y, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
+    return h + _drop(F.linear(y, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"]), p_hidden)
 
 
-def forward_lowres(sd, x, cfg):
-    """CE:246-257: backbone (TF:428-458, pooler result unused), drop CLS, NCHW view, seg_head."""
-    h = embeddings(sd, x, cfg)
+def forward_lowres(sd, x, cfg, dropout=(0.0, 0.0)):
+    """CE:246-257: backbone (TF:428-458, pooler result unused), drop CLS, NCHW view, seg_head.
+    dropout = (hidden_dropout_prob, attention_probs_dropout_prob) of the train-mode forward (CE:233-234: 0.1 / 0.1)."""
+    h = embeddings(sd, x, cfg, dropout[0])
     for i in range(cfg.num_hidden_layers):
-        h = encoder_layer(sd, h, i, cfg)
+        h = encoder_layer(sd, h, i, cfg, dropout[0], dropout[1])
     D = cfg.hidden_size
     h = F.layer_norm(h, (D,), sd["backbone.layernorm.weight"], sd["backbone.layernorm.bias"], cfg.layer_norm_eps)
     h = h[:, 1:, :]
@@ -158,9 +165,9 @@ def upsample(low, size):
     return F.interpolate(low, size=(size, size), mode="bilinear", align_corners=False)
 
 
-def forward(sd, x, cfg):
+def forward(sd, x, cfg, dropout=(0.0, 0.0)):
     """CE:246-262: ViTSegmentationModel.forward."""
-    return upsample(forward_lowres(sd, x, cfg), x.shape[-1])
+    return upsample(forward_lowres(sd, x, cfg, dropout), x.shape[-1])
 
 
 # ------------------------------------------------------------------------------------------------------------
