@@ -141,3 +141,30 @@ def test_bucket_ranges_partition_the_arena():
     assert covered[0][0] == 0 and covered[-1][1] == off
     for (s0, e0), (s1, e1) in zip(covered, covered[1:]):
         assert e0 == s1
+
+
+def _metric_counts_job(rank, world):
+    """Each rank holds the pixel counts of its shard of the batch; the global metrics come from the summed counts."""
+    from visiontransformer_b200 import metrics as M
+    g = torch.Generator().manual_seed(7)
+    pred = torch.randint(0, 5, (4, 24, 24), generator=g)
+    tgt = torch.randint(0, 5, (4, 24, 24), generator=g)
+
+    def counts(p, t):
+        out = torch.zeros(p.shape[0], 5, 3, dtype=torch.int32)
+        for c in range(5):
+            out[:, c, 0] = ((p == c) & (t == c)).flatten(1).sum(1)
+            out[:, c, 1] = (p == c).flatten(1).sum(1)
+            out[:, c, 2] = (t == c).flatten(1).sum(1)
+        return out
+    (ps, ts) = shard_batch((pred, tgt), rank, world)
+    tot = M.all_reduce_sum_counts(counts(ps, ts))
+    return tot, M.pixel_accuracy(tot), counts(pred, tgt).sum(0, keepdim=True).to(torch.int64)
+
+
+def test_metric_counts_all_reduce_to_the_global_batch_counts():
+    out = _run(_metric_counts_job)
+    for r in (0, 1):
+        tot, acc, want = out[r]
+        assert torch.equal(tot, want)
+        assert abs(acc.item() - (want[0, :, 0].sum() / want[0, :, 1].sum()).item()) < 1e-7
