@@ -147,7 +147,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -349,7 +349,7 @@ def run_ours(args):
                           "note": "eval forward of the same model: [B,17,224,224] fp32 logits (module contract) / fused uint8 mask"},
             "final_loss": losses[-1] if losses else None,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         # NCCL communicators captured into the CUDA graph: tear down explicitly and leave without the
         # process-group destructor (it can wait forever on the captured work objects)
@@ -359,6 +359,16 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+_STDOUT_FD = None
+
+
+def _emit(line: dict) -> None:
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -372,6 +382,12 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.1, help="hidden/attention dropout (reference default 0.1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library writes to file descriptor 1 while the benchmark runs
+    # (NCCL's version banner, for one) is sent to stderr instead; _emit() restores the descriptor for the result.
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
