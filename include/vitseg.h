@@ -166,6 +166,9 @@ int vs_upsample_bilinear_fwd(const float* low, float* full, int32_t B, int32_t C
 int vs_upsample_bilinear_bwd(const float* dfull, float* dlow, int32_t B, int32_t C, int32_t g, int32_t S,
                              void* stream);
 int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, int32_t C, int32_t g, int32_t S, void* stream);
+/* class ids -> RGB through a [C,3] uint8 palette (colored_pred = index_to_color[pred_labels],
+ *   model/CE/testViTModel.py:139-143): mask uint8 [n] -> rgb uint8 [n,3]; ids >= C map to black. */
+int vs_colorize_mask(const uint8_t* mask, const uint8_t* palette, uint8_t* rgb, int64_t n, int32_t C, void* stream);
 /* _argmax_stats: the same class map (mask may be NULL) plus exact per-image, per-class pixel counts against int64
  *   labels [B,S,S]: counts int32 [B, NC, 3] = {intersection, predicted, target}, NC = C (2 for C == 1); overwritten.
  *   Labels outside [0, NC) are not counted as targets.  Pixel accuracy / IoU / Dice / precision / recall of

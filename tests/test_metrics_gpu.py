@@ -86,3 +86,20 @@ def test_sdf_targets_are_bit_identical_to_compute_sdf(S):
     for b in range(masks.shape[0]):
         assert torch.equal(ext[b].cpu(), torch.from_numpy(ref[b][0])), ("ext", b)
         assert torch.equal(inn[b].cpu(), torch.from_numpy(ref[b][1])), ("int", b)
+
+
+def test_colorize_mask_is_the_palette_lookup():
+    """vs_colorize_mask == index_to_color[pred_labels] (model/CE/testViTModel.py:139-143), byte-exact, odd sizes."""
+    from visiontransformer_b200 import kernels as K
+    from visiontransformer_b200.ce.classes import ViTSegmentationModel
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    palette = torch.randint(0, 256, (17, 3), generator=g, dtype=torch.uint8)
+    for shape in ((2, 224, 224), (1, 7, 9), (3, 5)):
+        mask = torch.randint(0, 17, shape, generator=g, dtype=torch.uint8)
+        rgb = K.colorize_mask(mask.to(dev), palette.to(dev))
+        assert torch.equal(rgb.cpu(), palette[mask.long()])
+    m = ViTSegmentationModel(17, 16, 128, 1, 2).to(dev).eval()
+    x = torch.rand(2, 3, 224, 224, device=dev)
+    img = m.predict_colored(x, palette.to(dev))
+    assert img.shape == (2, 224, 224, 3) and torch.equal(img.cpu(), palette[m.predict_mask(x).long().cpu()])

@@ -181,6 +181,33 @@ upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask
   }
 }
 
+// class map -> colour image through the class palette: colored_pred = index_to_color[pred_labels]
+// (model/CE/testViTModel.py:139-143; the mask_image the worker posts back, backend/core/views.py:116-149).
+// uint8 [n] class ids -> uint8 [n, 3] RGB; 4 pixels (12 output bytes = three 32-bit words) per thread.
+__global__ void __launch_bounds__(256)
+colorize_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ palette, uint8_t* __restrict__ rgb,
+                long long n, int C) {
+  __shared__ uint8_t s_pal[256 * 3];
+  for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) s_pal[i] = i < C * 3 ? palette[i] : 0;
+  __syncthreads();
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uchar4 m = reinterpret_cast<const uchar4*>(mask)[i];
+    const uint8_t* a = s_pal + 3 * m.x;
+    const uint8_t* b = s_pal + 3 * m.y;
+    const uint8_t* c = s_pal + 3 * m.z;
+    const uint8_t* d = s_pal + 3 * m.w;
+    uint32_t* o = reinterpret_cast<uint32_t*>(rgb) + 3 * i;
+    o[0] = a[0] | (a[1] << 8) | (a[2] << 16) | ((uint32_t)b[0] << 24);
+    o[1] = b[1] | (b[2] << 8) | (c[0] << 16) | ((uint32_t)c[1] << 24);
+    o[2] = c[2] | (d[0] << 8) | (d[1] << 16) | ((uint32_t)d[2] << 24);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    for (int k = 0; k < 3; ++k) rgb[3 * i + k] = s_pal[3 * mask[i] + k];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused upsample + argmax + segmentation statistics: the predicted class map AND, per image and
 // class, the exact pixel counts  counts[b][c] = {intersection, predicted, target}  from which pixel accuracy, IoU, Dice,
@@ -838,6 +865,20 @@ extern "C" int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, in
     smem_set = smem;
   }
   upsample_argmax_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(low, mask, C, g, S, chunks);
+  VS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vs_colorize_mask(const uint8_t* mask, const uint8_t* palette, uint8_t* rgb, int64_t n, int32_t C,
+                                void* stream) {
+  VS_CHECK_ARG(mask && palette && rgb && n > 0 && C > 0 && C <= 256, "vs_colorize_mask: bad arguments");
+  VS_CHECK_ARG(((uintptr_t)mask % 4 == 0) && ((uintptr_t)rgb % 4 == 0), "vs_colorize_mask: mask / rgb must be 4-byte aligned");
+  const int nsm = sm_count();
+  VS_CHECK_ARG(nsm > 0, "vs_colorize_mask: no CUDA device");
+  long long nb = (n / 4 + 255) / 256;
+  if (nb > (long long)nsm * 16) nb = (long long)nsm * 16;
+  if (nb < 1) nb = 1;
+  colorize_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(mask, palette, rgb, n, C);
   VS_CHECK_LAUNCH();
   return 0;
 }

@@ -261,6 +261,18 @@ def upsample_argmax_stats(low, labels, size, mask=None):
     return counts
 
 
+def colorize_mask(mask, palette):
+    """uint8 class map [...], uint8 palette [C,3] -> uint8 RGB image [..., 3]."""
+    require_cuda(mask, "colorize_mask")
+    assert mask.dtype == torch.uint8 and mask.is_contiguous()
+    assert palette.dtype == torch.uint8 and palette.is_contiguous() and palette.dim() == 2 and palette.shape[1] == 3
+    rgb = torch.empty(*mask.shape, 3, device=mask.device, dtype=torch.uint8)
+    _count(1)
+    check(_lib.load().vs_colorize_mask(ptr(mask), ptr(palette), ptr(rgb), mask.numel(), palette.shape[0], stream()),
+          "vs_colorize_mask")
+    return rgb
+
+
 def sdf_targets(mask):
     """mask fp32 [B,S,S] (object > 0.5) -> (sdf_ext, sdf_int) fp32 [B,S,S]: compute_sdf of every image, on the device."""
     require_cuda(mask, "sdf_targets")

@@ -222,6 +222,13 @@ class ViTSegmentationModel(nn.Module):
         return K.upsample_argmax(low, mask)
 
 
+    @torch.no_grad()
+    def predict_colored(self, x: torch.Tensor, palette: torch.Tensor) -> torch.Tensor:
+        """uint8 RGB mask image [B,S,S,3] = palette[predict_mask(x)] (model/CE/testViTModel.py:139-143: the image the
+        inference worker posts back); palette uint8 [num_classes (2 for a binary head), 3] on the same device."""
+        return K.colorize_mask(self.predict_mask(x), palette.contiguous())
+
+
 def flops_per_image(cfg, train: bool) -> float:
     """Algorithmic FLOPs (2*MAC; GEMM/conv/attention only) per image — BASELINE.md §4."""
     P, D, L, I, C = cfg.patch_size, cfg.hidden_size, cfg.num_hidden_layers, cfg.intermediate_size, cfg.num_classes
