@@ -554,8 +554,11 @@ static TileChoice choose_tiles(int M, int N, int kblocks, int nsm, bool allow_sp
       const int work = tm * tn * s;
       const int waves = (work + units - 1) / units;
       const int kb = (kblocks + s - 1) / s;
-      // fixed per-work-item overhead (pipeline fill + epilogue drain) expressed in k-blocks
-      double cost = double(waves) * bn * (kb + 6.0);
+      // per-work-item time ~ columns x (k-blocks + fill/drain overhead); 128-wide tiles re-read A more often.
+      // Constants fitted to the measured table of tools/gemm_bench.py over the ViT-B/16 shapes x 5 configurations
+      // (r01: the first constants, overhead 6 / no width penalty, mis-picked pair128 for the QKV projection
+      // (47.3 vs 42.1 us) and for the fc2 weight gradient (52.2 vs 48.2 us)).
+      double cost = double(waves) * bn * (bn == 128 ? 1.05 : 1.0) * (kb + 1.5);
       if (!cta2) cost *= 1.02;  // prefer pairs on ties (less L2 traffic)
       if (cost < best_cost) { best_cost = cost; best = {cta2, bn, s}; }
     }
