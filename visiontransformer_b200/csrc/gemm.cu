@@ -17,6 +17,10 @@
 // Operands can be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) so the dgrad (dY·W) and wgrad
 // (dYᵀ·X) GEMMs of the backward pass read forward tensors in place (replaces autograd's mm_backward for
 // TF:216-218,262,290,305).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/vitseg.h"
 
@@ -596,7 +600,30 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.kblocks = (d->K + BK - 1) / BK;
   // tile_cfg: 0 automatic; 1..5 force {pair256, pair192, pair128, single256, single128} (tests / tuning)
-  const int forced_cfg = (d->tile_cfg >= 1 && d->tile_cfg <= 5) ? d->tile_cfg - 1 : -1;
+  int forced_cfg = (d->tile_cfg >= 1 && d->tile_cfg <= 5) ? d->tile_cfg - 1 : -1;
+  if (forced_cfg < 0) {
+    // tuning knob: VS_GEMM_TILE="M,N,K,a_mn,b_mn:cfg;..." forces a tile configuration (1..5) for the listed shapes, so
+    // that candidates can be compared inside the real training step rather than in an isolated micro-benchmark
+    static int n_over = -1;
+    static int over[16][6];
+    if (n_over < 0) {
+      n_over = 0;
+      const char* e = getenv("VS_GEMM_TILE");
+      while (e && *e && n_over < 16) {
+        int v[6];
+        if (sscanf(e, "%d,%d,%d,%d,%d:%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6) {
+          for (int i = 0; i < 6; ++i) over[n_over][i] = v[i];
+          ++n_over;
+        }
+        e = strchr(e, ';');
+        if (e) ++e;
+      }
+    }
+    for (int i = 0; i < n_over; ++i)
+      if (over[i][0] == d->M && over[i][1] == d->N && over[i][2] == d->K && over[i][3] == (d->a_mn_major != 0) &&
+          over[i][4] == (d->b_mn_major != 0) && over[i][5] >= 1 && over[i][5] <= 5)
+        forced_cfg = over[i][5] - 1;
+  }
   TileChoice tc = choose_tiles(d->M, d->N, p.kblocks, nsm, d->accumulate != 0, d->split_k, forced_cfg);
   int splits = tc.splits;
   if (splits > p.kblocks) splits = p.kblocks;
