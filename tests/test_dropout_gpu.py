@@ -230,3 +230,26 @@ def test_training_step_with_dropout_matches_masked_reference():
         # key biases have an exactly-zero true gradient (softmax shift invariance): absolute floor for such tensors
         err = (g.cpu() - v.grad).abs().max().item()
         assert err <= 4e-2 * v.grad.abs().max().item() + 2e-5, (k, err, v.grad.abs().max().item())
+
+
+def test_attention_dropout_index_space_is_independent_of_the_batch():
+    """Patch-4 scale (N = 3137) with batch*heads = 456: B*H*N*(N+1) exceeds 2^32, which the mask index used to
+    overflow.  The mask is seeded per (batch, head), so a batch entry gets the same mask wherever it sits... in its own
+    (batch, head) slot: slot 0 of a 1-image call equals slot 0 of the big call."""
+    from visiontransformer_b200 import kernels as K
+    dev = _dev()
+    B, N, H = 38, 3137, 12
+    torch.manual_seed(0)
+    qkv = (torch.randn(B, N, 3, H, 64, device=dev) * 0.5).to(torch.bfloat16)
+    ctx = torch.empty(B, N, H, 64, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=dev)
+    seed = torch.tensor([11], device=dev, dtype=torch.int32)
+    K.attention_fwd(qkv, ctx, lse, B, N, H, 0.125, dropout=(0.1, seed, 1003))
+    assert torch.isfinite(ctx.float()).all() and torch.isfinite(lse).all()
+    ctx1 = torch.empty(1, N, H, 64, device=dev, dtype=torch.bfloat16)
+    lse1 = torch.empty(1, H, N, device=dev)
+    K.attention_fwd(qkv[:1].contiguous(), ctx1, lse1, 1, N, H, 0.125, dropout=(0.1, seed, 1003))
+    assert torch.equal(ctx1[0], ctx[0])          # (b, h) = (0, h) slots coincide in both calls
+    nodrop = torch.empty_like(ctx1)
+    K.attention_fwd(qkv[:1].contiguous(), nodrop, lse1, 1, N, H, 0.125)
+    assert not torch.equal(nodrop, ctx1)

@@ -193,10 +193,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint8_t* sP = smem + AttnFwdSmem::kP;
     float* s_max = reinterpret_cast<float*>(smem + AttnFwdSmem::kMax);   // [block parity][half][row]
     const float sl2 = scale * kLog2e;
-    const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    // mask(b, h, q, k): one hash per key pair, seeded per (batch, head) so that the element index stays below 2^32
+    // for any batch size (index = q * ceil(N/2) + k/2)
+    const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)(b * H + h), drop_seed(drop)) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
     const float lds = log2f(dscale);
-    const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);  // pair index base
+    const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);  // pair index base
     float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
     float o_acc[32];
 #pragma unroll
@@ -412,9 +414,9 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint8_t* sP = smem + AttnFwdShortSmem::kP;
     float* s_red = reinterpret_cast<float*>(smem + AttnFwdShortSmem::kRed);
     const float sl2 = scale * kLog2e;
-    const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)(b * H + h), drop_seed(drop)) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
-    const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);
+    const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
     // 16-column chunks [c_beg, c_end) of this thread's row: the two threads of a row split the key axis
     const int nch = NK >> 4;
     const int c_beg = half == 0 ? 0 : (nch + 1) >> 1;
@@ -729,7 +731,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
     uint8_t* sP = smem + AttnBwdSmem::kP;
     uint8_t* sDS = smem + AttnBwdSmem::kDS;
     const float sl2 = scale * kLog2e;
-    const uint32_t dseed = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const uint32_t dseed0 = drop.thresh != 0u ? drop_seed(drop) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
     uint32_t qn = 0;
     // per-row statistics of the NEXT query tile are requested while this one waits for its MMAs
@@ -752,11 +754,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
       const int nvalid_kv = min(kKB, N - kv0);
       const int ncols = (nvalid_kv + 15) & ~15;
       const bool tail_block = nvalid_kv < kKB;
+      const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)bh, dseed0) : 0u;   // per (batch, head)
       for (int i = 0; i < nq; ++i, ++qn) {
         const uint32_t ph = qn & 1;
         const int q = i * kBQ + r;
         const bool q_ok = q < N;
-        const uint32_t drow = ((uint32_t)(b * H + h) * (uint32_t)N + (uint32_t)q) * (uint32_t)((N + 1) >> 1);
+        const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
         const float lse2 = lse_n * kLog2e, dlt = dlt_n;
         mbar_wait(bar_s, ph);
         tc_fence_after();
@@ -867,7 +870,7 @@ static int make_drop(DropCfg* dc, float p, const uint32_t* seed, uint32_t site, 
   dc->thresh = 0u; dc->scale = 1.0f; dc->seed = nullptr; dc->site = 0u;
   if (p > 0.0f) {
     if (!(p < 1.0f) || seed == nullptr || index_space >= (1LL << 32)) {
-      set_error("attention dropout: need 0<p<1, a device seed pointer and B*H*N*N < 2^32");
+      set_error("attention dropout: need 0<p<1, a device seed pointer and N*(N+1) < 2^32");
       return -1;
     }
     dc->thresh = (uint32_t)(p * 65536.0f + 0.5f);
@@ -903,7 +906,7 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
       attr_short = true;
     }
     DropCfg dcs;
-    if (int rc2 = make_drop(&dcs, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
+    if (int rc2 = make_drop(&dcs, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
     dim3 grid_s((N + kBQ - 1) / kBQ, H, B);
     attn_fwd_short_kernel<<<grid_s, kFwdThreads, AttnFwdShortSmem::kTotal, (cudaStream_t)stream>>>(
         tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dcs);
@@ -919,7 +922,7 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
     attr_stream = true;
   }
   DropCfg dc;
-  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
+  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
   attn_fwd_kernel<2><<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx, lse,
                                                                                        B, N, H, scale, dc);
@@ -953,7 +956,7 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   }
   VS_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * N * D * sizeof(float), st));
   DropCfg dc;
-  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)B * H * N * (N + 1))) return rc2;
+  if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
   {
     const long long rows = (long long)B * N * H;
     attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)ctx,
