@@ -5,7 +5,8 @@ reference's optional imports that are absent here (lightning, segmentation_model
 matplotlib) are stubbed in sys.modules — none of them is on the arithmetic path.  No
 reference source is copied: the classes are imported from where they lie.
 
-usage: python oracle/make_golden.py
+usage: python oracle/make_golden.py            (everything)
+       python oracle/make_golden.py --headline (only the headline-size training-step goldens)
 """
 from __future__ import annotations
 
@@ -221,5 +222,95 @@ def main():
     print("s384 golden written")
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# headline-size TRAINING-STEP goldens (round 2): ViT-B/16 (768/12/12) for the three training wrappers, and the
+# reference's own PAED configuration, PAEDTrainer(patch 8, hidden 1024, 16 layers, 16 heads) (PAED/ViTscript.py:66)
+# ---------------------------------------------------------------------------------------------------------------------
+def _pinned_grads(module, loss, L):
+    module.zero_grad()
+    loss.backward()
+    named = dict(module.named_parameters())
+    g = {}
+    for k, idx in O.headline_grad_pins(L):
+        g[k] = named[k].grad.detach()[idx].clone()
+    g["__total_sq__"] = sum(float((p.grad.double() ** 2).sum()) for p in module.parameters() if p.grad is not None)
+    g["__pooler_has_grad__"] = named["model.backbone.pooler.dense.weight"].grad is not None
+    return g
+
+
+def headline():
+    import builtins
+    import time
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 8)
+    ce = load_reference("CE")
+    paed = load_reference("PAED")
+    real_print = builtins.print
+    zero = lambda *a, **k: torch.zeros(1)  # noqa: E731
+    paed.segmentation_metrics = types.SimpleNamespace(mean_iou=zero)
+    paed.classification_metrics = types.SimpleNamespace(precision=zero, recall=zero)
+
+    # ---- ViT-B/16, B = 2: CE, multi-class PAED (C = 17), PAEDTrainer (C = 1)
+    t0 = time.time()
+    cfgb = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=768, num_hidden_layers=12, num_attention_heads=12)
+    sdb = O.seeded_state_dict(cfgb, seed=0, head_gain=4.0)
+    xb = O.synthetic_images(2, 224, seed=1234)
+    yb = O.synthetic_labels(2, 17, seed=1235)
+    out = {"cfg": cfgb.__dict__, "weights_seed": 0, "head_gain": 4.0, "image_seed": 1234, "label_seed": 1235}
+    ref = ce.LightningViTModel(17, 16, 768, 12, 12)
+    ref.load_state_dict(O.to_module_state_dict(sdb, "model."), strict=True)
+    ref.eval()   # dropout off (parity protocol)
+    loss = ref.training_step((xb, yb), 0)
+    out["ce_loss"] = loss.item()
+    out["ce_grads"] = _pinned_grads(ref, loss, 12)
+    del ref
+    builtins.print = lambda *a, **k: None
+    try:
+        refp = paed.LightningViTModel(17, 16, 768, 12, 12)
+        refp.load_state_dict(O.to_module_state_dict(sdb, "model."), strict=True)
+        refp.eval()
+        loss = refp.training_step((xb, yb), 0)
+    finally:
+        builtins.print = real_print
+    out["paed_multi_loss"] = loss.item()
+    out["paed_multi_grads"] = _pinned_grads(refp, loss, 12)
+    del refp
+    cfg1 = O.OracleConfig(num_classes=1, patch_size=16, hidden_size=768, num_hidden_layers=12, num_attention_heads=12)
+    sd1 = O.seeded_state_dict(cfg1, seed=3, head_gain=8.0)
+    masks, sdf_e, sdf_i = O.synthetic_binary_targets(2, 224, seed=1236)
+    reft = paed.PAEDTrainer(1, 16, 768, 12, 12)
+    reft.load_state_dict(O.to_module_state_dict(sd1, "model."), strict=True)
+    reft.eval()
+    loss = reft.training_step((xb, masks, sdf_e, sdf_i), 0)
+    out["paed_bin"] = {"weights_seed": 3, "head_gain": 8.0, "target_seed": 1236, "loss": loss.item(),
+                       "grads": _pinned_grads(reft, loss, 12)}
+    del reft
+    torch.save(out, os.path.join(GOLD, "vitb16_train.pt"))
+    print(f"vitb16_train golden written ({time.time() - t0:.0f} s): ce {out['ce_loss']:.6f} paed_multi "
+          f"{out['paed_multi_loss']:.6f} paed_bin {out['paed_bin']['loss']:.6f}")
+
+    # ---- the reference's PAED model: PAEDTrainer(num_classes=1, patch 8, hidden 1024, 16 layers, 16 heads), B = 1
+    t0 = time.time()
+    cfg8 = O.OracleConfig(num_classes=1, patch_size=8, hidden_size=1024, num_hidden_layers=16, num_attention_heads=16)
+    sd8 = O.seeded_state_dict(cfg8, seed=5, head_gain=8.0)
+    x8 = O.synthetic_images(1, 224, seed=1237)
+    m8, e8, i8 = O.synthetic_binary_targets(1, 224, seed=1238)
+    ref8 = paed.PAEDTrainer(num_classes=1, patch_size=8, hidden_size=1024, num_hidden_layers=16, num_attention_heads=16)
+    ref8.load_state_dict(O.to_module_state_dict(sd8, "model."), strict=True)
+    ref8.eval()
+    cap = {}
+    ref8.model.seg_head.register_forward_hook(lambda m, i, o: cap.__setitem__("low", o.detach().clone()))
+    loss = ref8.training_step((x8, m8, e8, i8), 0)
+    o8 = {"cfg": cfg8.__dict__, "weights_seed": 5, "head_gain": 8.0, "image_seed": 1237, "target_seed": 1238,
+          "low": cap["low"], "loss": loss.item(), "grads": _pinned_grads(ref8, loss, 16)}
+    torch.save(o8, os.path.join(GOLD, "p8w1024_train.pt"))
+    print(f"p8w1024_train golden written ({time.time() - t0:.0f} s): paed_bin {o8['loss']:.6f}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--headline" in sys.argv:
+        headline()
+    else:
+        main()
+        headline()

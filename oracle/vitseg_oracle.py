@@ -291,5 +291,29 @@ def synthetic_binary_targets(B, S, seed=1236):
     return t(masks), t(se), t(si)
 
 
+# gradient pins of the headline-size training-step goldens (tests/golden/vitb16_train.pt, p8w1024_train.pt): (parameter, index expression applied to its .grad) spanning head / last layer / first layer /
+# embeddings; big matrices are strided so the fixture stays small
+def headline_grad_pins(L: int):
+    last = L - 1
+    return [
+        ("model.seg_head.2.weight", (slice(None),) * 4),
+        ("model.seg_head.0.bias", (slice(None),)),
+        ("model.seg_head.0.weight", (slice(None, None, 16), slice(None, None, 24))),
+        ("model.backbone.layernorm.weight", (slice(None),)),
+        (f"model.backbone.encoder.layer.{last}.output.dense.bias", (slice(None),)),
+        (f"model.backbone.encoder.layer.{last}.intermediate.dense.weight", (slice(None, None, 48), slice(None, None, 12))),
+        (f"model.backbone.encoder.layer.{last}.attention.attention.value.weight", (slice(None, None, 12), slice(None, None, 12))),
+        (f"model.backbone.encoder.layer.{L // 2}.attention.output.dense.weight", (slice(None, None, 12), slice(None, None, 12))),
+        ("model.backbone.encoder.layer.0.attention.attention.query.weight", (slice(None, None, 12), slice(None, None, 12))),
+        ("model.backbone.encoder.layer.0.attention.attention.query.bias", (slice(None),)),
+        ("model.backbone.encoder.layer.0.layernorm_before.weight", (slice(None),)),
+        ("model.backbone.encoder.layer.0.output.dense.weight", (slice(None, None, 12), slice(None, None, 48))),
+        ("model.backbone.embeddings.cls_token", (slice(None),) * 3),
+        ("model.backbone.embeddings.position_embeddings", (slice(None), slice(None, None, 7), slice(None, None, 8))),
+        ("model.backbone.embeddings.patch_embeddings.projection.weight", (slice(None, None, 8),)),
+        ("model.backbone.embeddings.patch_embeddings.projection.bias", (slice(None),)),
+    ]
+
+
 def to_module_state_dict(sd, prefix=""):
     return {prefix + k: v.clone() for k, v in sd.items()}

@@ -130,3 +130,70 @@ def test_image_size_384_matches_reference(golden_dir):
     with torch.no_grad():
         full = O.forward(sd, x, cfg)
     assert _rel(full[:, :, ::11, ::11], gold["logits_sub"]) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# headline-size training-step goldens (round 2): the reference's loss and pinned gradient slices at ViT-B/16 and at the
+# reference's own PAED configuration (patch 8, hidden 1024, 16 layers, 16 heads: PAED/ViTscript.py:66)
+# ---------------------------------------------------------------------------------------------------------------------
+def _pinned(sd, loss_fn, L, gold):
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss = loss_fn(leaves)
+    loss.backward()
+    for k, idx in O.headline_grad_pins(L):
+        got = leaves[k[len("model."):]].grad[idx]
+        assert got.shape == gold[k].shape, k
+        assert _rel(got, gold[k]) < 3e-4, (k, _rel(got, gold[k]))
+    total = sum(float((v.grad.double() ** 2).sum()) for v in leaves.values() if v.grad is not None)
+    assert abs(total - gold["__total_sq__"]) < 1e-3 * gold["__total_sq__"]
+    assert not gold["__pooler_has_grad__"] and leaves["backbone.pooler.dense.weight"].grad is None
+    return loss.item()
+
+
+@pytest.fixture(scope="module")
+def vitb_train(golden_dir):
+    return torch.load(os.path.join(golden_dir, "vitb16_train.pt"), weights_only=False)
+
+
+def test_vitb16_ce_training_step_matches_reference(vitb_train):
+    g = vitb_train
+    cfg = O.OracleConfig(**g["cfg"])
+    sd = O.seeded_state_dict(cfg, g["weights_seed"], head_gain=g["head_gain"])
+    x = O.synthetic_images(2, 224, seed=g["image_seed"])
+    y = O.resize_target(O.synthetic_labels(2, 17, seed=g["label_seed"]), 224)
+    loss = _pinned(sd, lambda p: O.ce_loss(O.forward(p, x, cfg), y), 12, g["ce_grads"])
+    assert abs(loss - g["ce_loss"]) < 2e-5 * abs(g["ce_loss"])
+
+
+def test_vitb16_paed_multiclass_training_step_matches_reference(vitb_train):
+    g = vitb_train
+    cfg = O.OracleConfig(**g["cfg"])
+    sd = O.seeded_state_dict(cfg, g["weights_seed"], head_gain=g["head_gain"])
+    x = O.synthetic_images(2, 224, seed=g["image_seed"])
+    y = O.resize_target(O.synthetic_labels(2, 17, seed=g["label_seed"]), 224)
+    loss = _pinned(sd, lambda p: O.paed_multiclass_step_loss(O.forward(p, x, cfg), y), 12, g["paed_multi_grads"])
+    assert abs(loss - g["paed_multi_loss"]) < 5e-5 * abs(g["paed_multi_loss"])
+
+
+def test_vitb16_paed_trainer_step_matches_reference(vitb_train):
+    g, pb = vitb_train, vitb_train["paed_bin"]
+    cfg = O.OracleConfig(num_classes=1, patch_size=16, hidden_size=768, num_hidden_layers=12, num_attention_heads=12)
+    sd = O.seeded_state_dict(cfg, pb["weights_seed"], head_gain=pb["head_gain"])
+    x = O.synthetic_images(2, 224, seed=g["image_seed"])
+    masks, se, si = O.synthetic_binary_targets(2, 224, seed=pb["target_seed"])
+    loss = _pinned(sd, lambda p: O.paed_binary_step_loss(O.forward(p, x, cfg), O.resize_target(masks, 224), se, si),
+                   12, pb["grads"])
+    assert abs(loss - pb["loss"]) < 2e-5 * abs(pb["loss"])
+
+
+def test_p8_w1024_paed_trainer_step_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "p8w1024_train.pt"), weights_only=False)
+    cfg = O.OracleConfig(**g["cfg"])
+    sd = O.seeded_state_dict(cfg, g["weights_seed"], head_gain=g["head_gain"])
+    x = O.synthetic_images(1, 224, seed=g["image_seed"])
+    masks, se, si = O.synthetic_binary_targets(1, 224, seed=g["target_seed"])
+    with torch.no_grad():
+        assert _rel(O.forward_lowres(sd, x, cfg), g["low"]) < 5e-5
+    loss = _pinned(sd, lambda p: O.paed_binary_step_loss(O.forward(p, x, cfg), O.resize_target(masks, 224), se, si),
+                   16, g["grads"])
+    assert abs(loss - g["loss"]) < 2e-5 * abs(g["loss"])

@@ -219,8 +219,8 @@ def test_wrong_size_and_small_patch_variants():
 
 def test_ce_loss_curve_tracks_oracle():
     """Loop-level parity: Adam steps on a learnable synthetic task, dropout off; per-step loss within 1 % of the fp32
-    oracle trained from the same weights (north_star: loss curve within 1 %).  60 steps of a 2-layer model keep the
-    CPU oracle side within the GPU-box time budget; bench/DESIGN.md record the 200-step ViT-B/16 run."""
+    oracle trained from the same weights (north_star: loss curve within 1 %).  This is the quick 60-step check on a
+    2-layer model; the 200-step ViT-B/16 run is tests/test_headline_gpu.py::test_vitb16_200_step_loss_curve_and_trained_argmax."""
     from visiontransformer_b200.ce.classes import LightningViTModel
     dev = _dev()
     torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
