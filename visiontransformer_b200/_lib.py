@@ -81,6 +81,25 @@ _SIGS = {
 EXPORTED_SYMBOLS = tuple(["vs_last_error", *_SIGS.keys()])
 
 
+def _preload_cudart() -> None:
+    """libvitseg.so links the CUDA runtime dynamically (libcudart.so.12).  `import torch` has normally mapped it
+    already; if the loader cannot find it by name, take the copy that ships next to torch."""
+    try:
+        C.CDLL("libcudart.so.12", mode=C.RTLD_GLOBAL)
+        return
+    except OSError:
+        pass
+    import glob
+    import sys
+    for base in sys.path:
+        for cand in glob.glob(os.path.join(base, "nvidia", "cuda_runtime", "lib", "libcudart.so.12*")):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+            except OSError:
+                continue
+
+
 def load() -> C.CDLL:
     """Loads libvitseg.so (building it is __graft_entry__.build()'s job).  Raises if it is missing."""
     global _lib
@@ -90,6 +109,7 @@ def load() -> C.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} not found: build it with `python -m visiontransformer_b200.build` "
             "(there is no CPU or PyTorch fallback for the ViT-segmentation kernels)")
+    _preload_cudart()
     lib = C.CDLL(LIB_PATH)
     lib.vs_last_error.restype = C.c_char_p
     lib.vs_last_error.argtypes = []

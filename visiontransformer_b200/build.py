@@ -77,7 +77,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and log:
                     print(log)
     if jobs or not os.path.exists(LIBPATH):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIBPATH, *objs]
+        # --cudart shared: the library uses the process's libcudart.so.12 (the one torch has already loaded) instead
+        # of embedding a private static copy of the whole runtime (smaller artefact, one runtime per process)
+        cmd = [nvcc, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIBPATH, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

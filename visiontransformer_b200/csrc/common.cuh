@@ -151,8 +151,10 @@ struct DropCfg {
   const uint32_t* seed;   // device pointer: per-step counter (CUDA-graph replays advance it on the device)
   uint32_t site;
 };
+__device__ __forceinline__ uint32_t drop_hash(uint32_t x, uint32_t seed);
+// (step, site) -> seed through two full avalanche rounds: seeds of neighbouring steps / sites share no linear relation
 __device__ __forceinline__ uint32_t drop_seed(const DropCfg& d) {
-  return d.seed[0] * 0x9E3779B9u + d.site * 0x85EBCA6Bu + 0x27D4EB2Fu;
+  return drop_hash(d.site + 0x27D4EB2Fu, drop_hash(d.seed[0], 0x9E3779B9u));
 }
 __device__ __forceinline__ uint32_t drop_hash(uint32_t x, uint32_t seed) {
   x ^= seed;

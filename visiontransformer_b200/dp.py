@@ -124,6 +124,7 @@ class DataParallel:
         loss.backward()
         if sync_grads and self.world > 1:
             self._reducer.finish()
+        eng.finish_foreign_grads()
         eng.grad_ready_hook = None
         if sync_grads and self.optimizer is not None:
             self.optimizer.step()

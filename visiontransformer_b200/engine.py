@@ -20,6 +20,7 @@ import math
 from typing import Dict, List, Optional
 
 import torch
+import torch.distributed
 
 from . import kernels as K
 
@@ -81,6 +82,7 @@ class Engine:
         self._grads_zeroed = False   # set by FusedAdam: gradient arena already zero
         self._ws: Dict = {}
         self._saved = None
+        self._foreign = []
         self.grad_ready_hook = None  # callable(bucket_name) used by the data-parallel wrapper
         self.rng_step = None         # device uint32 counter: advances once per dropout-enabled forward (graph-safe)
         self._drop = (0.0, 0.0)      # (hidden p, attention p) used by the last training forward
@@ -283,11 +285,17 @@ class Engine:
         g, T1, M = ws["g"], ws["T1"], ws["M"]
         scale = 1.0 / math.sqrt(D // H)
         n = 0
-        p_hid = float(cfg.hidden_dropout_prob) if (dropout and train) else 0.0
-        p_att = float(cfg.attention_probs_dropout_prob) if (dropout and train) else 0.0
+        # dropout follows module.training as in the reference, also on a no-grad forward (train=False only means that
+        # no activations are saved for a backward pass)
+        p_hid = float(cfg.hidden_dropout_prob) if dropout else 0.0
+        p_att = float(cfg.attention_probs_dropout_prob) if dropout else 0.0
         if p_hid > 0.0 or p_att > 0.0:
             if self.rng_step is None or self.rng_step.device != x.device:
-                self.rng_step = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(x.device)
+                seed = int(torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64))
+                # data parallel: ranks that seeded the host generator identically must still draw independent masks
+                if torch.distributed.is_available() and torch.distributed.is_initialized():
+                    seed = (seed + torch.distributed.get_rank() * 0x3C6EF35F) & 0x7FFFFFFF
+                self.rng_step = torch.tensor([seed], dtype=torch.int32).to(x.device)
             self.rng_step.add_(1)   # device-side: a captured graph advances it on every replay
         if train:
             self._drop = (p_hid, p_att)
@@ -352,7 +360,10 @@ class Engine:
         params = self._named()
         base = self.grads.data_ptr()
         fresh = all(p.grad is None for p in params.values())
-        if fresh and not self._grads_zeroed:
+        frozen = any(not p.requires_grad for p in params.values())
+        # frozen parameters: the backward kernels still write their arena slots (the GEMM sequence is fixed), but the
+        # slots are never exposed as .grad and never reach an optimizer; they are cleared with the rest every step
+        if fresh and (frozen or not self._grads_zeroed):
             self.grads.zero_()
             self.launches += 1
         self._grads_zeroed = False
@@ -360,6 +371,8 @@ class Engine:
         for n, p in params.items():
             if n.startswith("backbone.pooler."):
                 continue  # dead compute in the reference forward (TF:456 result unused): no gradient
+            if not p.requires_grad:
+                continue  # requires_grad=False: no .grad, as autograd would leave it
             s = self.slots[n]
             gview = self.grads[s.offset:s.offset + s.numel].view(s.shape)
             if p.grad is None:
@@ -466,6 +479,27 @@ class Engine:
         n += 2
         if hook:
             hook("embed")
-        for p_, gview, old in foreign:
-            old.add_(gview)
+        self._foreign = foreign
+        if not hook:
+            self.finish_foreign_grads()
         self.launches += n
+        self._fire_param_hooks()
+
+    def finish_foreign_grads(self):
+        """.grad tensors that do not alias the arena (set by the user / another optimizer) receive this backward's
+        gradient by addition.  Under data parallel this runs after the bucket all-reduces have completed
+        (DataParallel.step), never while a collective is still in flight on the arena slice."""
+        for p_, gview, old in getattr(self, "_foreign", ()):
+            old.add_(gview)
+        self._foreign = []
+
+    def _fire_param_hooks(self):
+        """Parameter gradients are produced by the engine, not by autograd's AccumulateGrad nodes, so hooks registered
+        with Tensor.register_post_accumulate_grad_hook are invoked here (once per backward, after all gradients are
+        final).  Hooks on the AccumulateGrad node itself (what torch DistributedDataParallel installs) cannot be
+        reached: use visiontransformer_b200.dp.DataParallel for multi-GPU training."""
+        for p in self.module.parameters():
+            hooks = getattr(p, "_post_accumulate_grad_hooks", None)
+            if hooks and p.grad is not None:
+                for h in list(hooks.values()):
+                    h(p)

@@ -131,12 +131,17 @@ class _PaedMulticlass(torch.autograd.Function):
 
 
 _SCRATCH = {}
+_RETIRED = []   # outgrown scratch buffers stay alive: a captured CUDA graph may have their addresses baked in
 
 
 def _scratch(device, numel, n):
-    key = (device, n)
+    """n fp32 scratch planes of >= numel elements, keyed by (device, stream, n): the buffers are stream-ordered
+    temporaries, so two streams never share one, and growing never frees what an earlier capture recorded."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream, n)
     cur = _SCRATCH.get(key)
     if cur is None or cur[0].numel() < numel:
+        if cur is not None:
+            _RETIRED.append(cur)
         cur = [torch.empty(numel, device=device, dtype=F32) for _ in range(n)]
         _SCRATCH[key] = cur
     return cur

@@ -206,7 +206,7 @@ class ViTSegmentationModel(nn.Module):
         if needs_grad:
             anchor = self.seg_head[2].bias
             return _LowresFn.apply(x, anchor, self._engine, self._dropout_active())
-        return self._engine.forward_lowres(x, train=False)
+        return self._engine.forward_lowres(x, train=False, dropout=self._dropout_active())
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """[B,3,S,S] fp32 -> logits [B,C,S,S] fp32 (model/CE/classes.py:246-262)."""

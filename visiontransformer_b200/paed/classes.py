@@ -93,9 +93,32 @@ class PAEDTrainer(LightningModule):
     def forward(self, x):
         return self.model(x)
 
+    # dice_loss / paed_loss_soft: the reference defines them as methods on DENSE [B,1,H,W] probability tensors and its own
+    # _forward_step_paed calls them (model/PAED/classes.py:675-679).  The training step here never does — it takes
+    # the fused low-resolution kernels (paed_binary_loss) — but a user subclass that overrides the step and calls
+    # them, as the reference does, must keep working: they are provided as differentiable device-tensor functions
+    # with the reference's arithmetic (a dozen elementwise / 3x3 ops on tensors the caller already materialised).
     def dice_loss(self, preds, targets, smooth=1e-6):
-        raise RuntimeError("PAEDTrainer.dice_loss is fused into the PAED-binary loss kernels; use "
-                           "visiontransformer_b200.losses.paed_binary_loss")
+        """model/PAED/classes.py:608-620."""
+        K.require_cuda(preds, "PAEDTrainer.dice_loss")
+        if targets.dim() == 3:
+            targets = targets.unsqueeze(1)
+        p, t = preds.float().reshape(-1), targets.float().reshape(-1)
+        return 1 - (2. * torch.sum(p * t) + smooth) / (p.sum() + t.sum() + smooth)
+
+    def paed_loss_soft(self, gt_sdf_ext, gt_sdf_int, preds):
+        """model/PAED/classes.py:623-661: preds [B,1,H,W] in [0,1]; gt_sdf_* [B,1,h,w] (bilinearly resized to H x W)."""
+        K.require_cuda(preds, "PAEDTrainer.paed_loss_soft")
+        B, _, H, W = preds.shape
+        gt_sdf_ext = F.interpolate(gt_sdf_ext, size=(H, W), mode='bilinear', align_corners=False)
+        gt_sdf_int = F.interpolate(gt_sdf_int, size=(H, W), mode='bilinear', align_corners=False)
+        sobel_x = torch.tensor([[1, 0, -1], [2, 0, -2], [1, 0, -1]], device=preds.device,
+                               dtype=torch.float32).view(1, 1, 3, 3)
+        grad_x = F.conv2d(preds, sobel_x, padding=1)
+        grad_y = F.conv2d(preds, sobel_x.transpose(2, 3), padding=1)
+        edge_map = torch.sqrt(grad_x ** 2 + grad_y ** 2 + 1e-6)
+        edge_map = edge_map / (edge_map.view(B, -1).max(dim=1)[0].view(B, 1, 1, 1) + 1e-6)
+        return 1 * (gt_sdf_ext * edge_map).mean() - 0.5 * (gt_sdf_int * preds).mean()
 
     def _forward_step(self, batch, batch_idx):
         return self._forward_step_paed(batch, batch_idx)
@@ -131,6 +154,15 @@ class PAEDTrainer(LightningModule):
         self.log_dict({"val_loss": loss, "val_acc": accuracy, "val_IoU": iou, "val_recall": recall, "val_dice": dice,
                        "val_precision": precision}, on_epoch=True)
         return loss
+
+    def test_step(self, batch, batch_idx):
+        """model/PAED/classes.py:524-531.  (The reference unpacks SEVEN values from a _forward_step that returns six
+        and so raises ValueError under trainer.test(); this returns the metrics it meant to log.)"""
+        _, accuracy, iou, dice, precision, recall = self._forward_step(batch, batch_idx)
+        metrics_ = {"test_acc": accuracy, "test_IoU": iou, "test_recall": recall, "test_dice": dice,
+                    "test_precision": precision}
+        self.log_dict(metrics_, on_epoch=True)
+        return metrics_
 
     def configure_optimizers(self):
         optimizer = AdamW(self.model.parameters(), lr=1e-4)
