@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 1
+#define VS_ABI_VERSION 2
 
 const char* vs_last_error(void);
 int vs_abi_version(void);
@@ -179,12 +179,15 @@ int vs_upsample_argmax_stats(const float* low, const int64_t* labels, uint8_t* m
 
 /* ------------------------------------------------------------------------------------------------
  * Fused upsample + cross-entropy (model/CE/classes.py:276-285: F.interpolate -> nn.CrossEntropyLoss, mean over
- * B*S*S, ignore_index -100).  labels int64 [B,S,S].
+ * B*S*S, ignore_index -100), with the label resize of model/CE/classes.py:273-274 folded into the label read.
+ *   labels [B, LH, LW], int64 (label_dtype 0, as the reference's dataset produces) or uint8 (label_dtype 1, 255 is NOT
+ *   an ignore value: only int64 -100 is).  LH x LW != S x S: the label of output pixel (y, x) is taken at
+ *   (min(floor(y * LH/S), LH-1), min(floor(x * LW/S), LW-1)), i.e. F.interpolate(mode='nearest') of the label map.
  *   loss_sum[0] += sum of per-pixel NLL, loss_sum[1] += number of non-ignored pixels   (caller zeroes)
  *   dlow (nullable) fp32 [B,C,g,g] = d(sum NLL)/d low  (caller zeroes; host scales by 1/count)
  * ------------------------------------------------------------------------------------------------ */
-int vs_upsample_ce(const float* low, const int64_t* labels, float* loss_sum, float* dlow, int32_t B, int32_t C,
-                   int32_t g, int32_t S, void* stream);
+int vs_upsample_ce(const float* low, const void* labels, int32_t label_dtype, int32_t LH, int32_t LW, float* loss_sum,
+                   float* dlow, int32_t B, int32_t C, int32_t g, int32_t S, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PAED binary loss (model/PAED/classes.py:608-701): p = sigmoid(up(low)), BCE, Dice sums, Sobel edge map,

@@ -7,6 +7,7 @@ reference source is copied: the classes are imported from where they lie.
 
 usage: python oracle/make_golden.py            (everything)
        python oracle/make_golden.py --headline (only the headline-size training-step goldens)
+       python oracle/make_golden.py --curve    (only the 200-step reference loss curves, ~10 min)
 """
 from __future__ import annotations
 
@@ -308,9 +309,46 @@ def headline():
     print(f"p8w1024_train golden written ({time.time() - t0:.0f} s): paed_bin {o8['loss']:.6f}")
 
 
+
+def curve(steps: int = 200):
+    """200 optimisation steps of the UNMODIFIED reference CE module with its own optimizer
+    (LightningViTModel.configure_optimizers: Adam lr 1e-5, CE:296-297) on fixed batches, dropout off: the loss curve the
+    CUDA path has to follow within 1 % per step (north_star)."""
+    import time
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 8)
+    ce = load_reference("CE")
+    cfgb = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=768, num_hidden_layers=12, num_attention_heads=12)
+    out = {"cfg": cfgb.__dict__, "weights_seed": 31, "head_gain": 1.0, "steps": steps, "optimizer": "Adam(lr=1e-5)"}
+    for task in ("regions", "brightness"):
+        t0 = time.time()
+        sd = O.seeded_state_dict(cfgb, seed=31, head_gain=1.0)
+        x, y = O.curve_task(task)
+        ref = ce.LightningViTModel(17, 16, 768, 12, 12)
+        ref.load_state_dict(O.to_module_state_dict(sd, "model."), strict=True)
+        ref.eval()   # dropout off; training_step / backward / optimizer are unaffected by eval()
+        opt = ref.configure_optimizers()
+        losses = []
+        for i in range(steps):
+            loss = ref.training_step((x, y), i)     # labels already 224x224: _resize_target is the identity
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+            if i % 20 == 0:
+                print(task, i, losses[-1], f"{time.time() - t0:.0f}s", flush=True)
+        out[task] = torch.tensor(losses, dtype=torch.float64)
+        del ref, opt
+    torch.save(out, os.path.join(GOLD, "vitb16_curve.pt"))
+    print("vitb16_curve golden written")
+
+
 if __name__ == "__main__":
-    if "--headline" in sys.argv:
+    if "--curve" in sys.argv:
+        curve()
+    elif "--headline" in sys.argv:
         headline()
     else:
         main()
         headline()
+        curve()

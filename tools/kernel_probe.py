@@ -119,6 +119,30 @@ def probe_gemm():
         case(12608, 768, 768, False, False, bias=True, res=True, f32=True, cfg=cfg)
         case(768, 3072, 4000, True, True, f32=True, acc=True, split_k=2, cfg=cfg)
 
+    # bf16 outputs (shared-memory staged TMA-store epilogue on the 256- / 128-column tiles, register-direct on 192):
+    # every tile configuration x {plain, bias + GELU + pre-activation copy, GELU' aux, ReLU-mask aux}, ragged M, a
+    # 16-column tail, several tiles per CTA (aux prefetch / buffer reuse across tiles)
+    for cfg in (1, 2, 3, 4, 5):
+        case(1000, 768, 832, False, False, cfg=cfg)
+        case(5000, 1024, 256, False, False, bias=True, act=1, out2=True, cfg=cfg)
+        case(5000, 1024, 256, False, True, aux_mode=1, cfg=cfg)
+        case(1000, 256, 512, False, True, aux_mode=2, bias=True, cfg=cfg)
+        case(300, 48, 128, False, True, cfg=cfg)
+        case(40000, 512, 64, False, False, bias=True, act=1, out2=True, cfg=cfg)
+
+    def strided_case():
+        # bf16 output / aux that are column slices of wider matrices (row stride != N), as the engine's views can be
+        M, N, Kd = 777, 256, 192
+        a = bf(torch.randn(M, Kd, device=dev))
+        b = bf(torch.randn(N, Kd, device=dev) * 0.5)
+        wide = torch.zeros(M, 3 * N, device=dev, dtype=torch.bfloat16)
+        auxw = bf(torch.randn(M, 2 * N, device=dev))
+        K.gemm(a, b, wide[:, N:2 * N], aux=auxw[:, N:], aux_mode=2)
+        ref = (a.float() @ b.float().t()) * (auxw[:, N:].float() > 0)
+        report("gemm bf16 strided out / aux views", rel(wide[:, N:2 * N], ref), 1e-2)
+        report("   neighbours untouched", float(wide[:, :N].abs().max() + wide[:, 2 * N:].abs().max()), 1e-30)
+    run("gemm strided", strided_case)
+
     def patch_case():
         Bn, T1, D, Kd = 3, 197, 768, 768
         a = bf(torch.randn(Bn * T1, Kd, device=dev))
@@ -309,7 +333,7 @@ def probe_loss():
                 labels[0, :3, :5] = -100
                 ls = torch.zeros(2, device=dev)
                 dl = torch.zeros_like(low)
-                K.upsample_ce(low, labels, ls, dl)
+                K.upsample_ce(low, labels, ls, dl, S)
                 lr.grad = None
                 lossr = F.cross_entropy(F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False), labels,
                                         reduction="sum")
@@ -317,6 +341,19 @@ def probe_loss():
                 report(f"upsample_ce loss {Bn},{Cn},{g},{S}", abs(ls[0].item() - lossr.item()) / lossr.item(), 1e-5)
                 report(f"upsample_ce count", abs(ls[1].item() - (labels != -100).sum().item()), 0.0)
                 report(f"upsample_ce dlow {Bn},{Cn},{g},{S}", rel(dl, lr.grad), 1e-4)
+                # labels at their stored resolution: the legacy-'nearest' resize (model/CE/classes.py:273-274) inside
+                # the kernel's label read, int64 and uint8
+                for LS, dt in ((256, torch.int64), (256, torch.uint8), (100, torch.int64)):
+                    lab = torch.randint(0, Cn, (Bn, LS, LS), device=dev)
+                    want = F.interpolate(lab[:, None].float(), size=(S, S), mode="nearest")[:, 0].long()
+                    ls2, dl2 = torch.zeros(2, device=dev), torch.zeros_like(low)
+                    K.upsample_ce(low, lab.to(dt), ls2, dl2, S)
+                    lr.grad = None
+                    l2 = F.cross_entropy(F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False), want,
+                                         reduction="sum")
+                    l2.backward()
+                    report(f"upsample_ce labels {LS}->{S} {dt} loss", abs(ls2[0].item() - l2.item()) / l2.item(), 1e-5)
+                    report(f"upsample_ce labels {LS}->{S} {dt} dlow", rel(dl2, lr.grad), 1e-4)
     run("loss/upsample", f)
 
     def paed_bin():

@@ -62,7 +62,7 @@ _SIGS = {
     "vs_colorize_mask": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p],
     "vs_sdf_workspace_bytes": [c_int, c_int],
     "vs_sdf_targets": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
-    "vs_upsample_ce": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "vs_upsample_ce": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_paed_binary_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vs_paed_binary_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                            c_void_p],

@@ -30,8 +30,9 @@ class LightningViTModel(LightningModule):
         return F.interpolate(y.unsqueeze(1).float(), size=size, mode='nearest').squeeze(1).long()
 
     def _loss(self, x, y):
+        # training_step of the reference: y = self._resize_target(y, size=(224, 224)); loss_fn(self(x), y).  Here the
+        # nearest-neighbour index map of _resize_target is applied inside the loss kernel's label read
         S = x.shape[-1]
-        y = self._resize_target(y, size=(S, S))
         low = self.model.forward_lowres(x)
         return upsample_cross_entropy(low, y, S)
 

@@ -38,6 +38,9 @@ int sm_count();
 // box[i] = box extent per dim; swizzle 128B; OOB elements are zero-filled.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// same with an explicit swizzle span in bytes (128, 64, 32 or 0 = none); box[0] * 2 must not exceed it
+int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------

@@ -50,19 +50,27 @@ struct GemmParams {
   DropCfg drop;  // hidden-state dropout applied to (acc + bias) before the residual add (fp32 outputs only)
 };
 
-template <int BN, int CTA2>
+// EPI = 0: register-direct / smem-transposed epilogues (fp32 outputs, accumulation, BN = 192).
+// EPI = 1: bf16 outputs leave through shared memory and cp.async.bulk.tensor stores: each epilogue warp owns one
+//          swizzled [32 rows x BN/4 columns] bf16 staging tile (4 KB for BN = 256), which also receives the GELU' / ReLU
+//          mask operand (aux) by TMA load ahead of the accumulator.
+template <int BN, int CTA2, int EPI>
 struct Cfg {
   static constexpr int kBNH = CTA2 ? BN / 2 : BN;                // B rows staged per CTA
   static constexpr int kBBoxes = (kBNH + 63) / 64;               // 64-wide MN-major boxes per CTA
   static constexpr int kABytes = BM * BK * 2;                    // 16 KB
   static constexpr int kBAlloc = kBBoxes * 64 * BK * 2;          // smem reserved for B per stage
   static constexpr int kStageBytes = kABytes + kBAlloc;
-  static constexpr int kEpiBytes = kEpiWarps * 2048;             // one swizzled 32x16 fp32 staging tile per warp
-  static constexpr int kStages = (222 * 1024 - kEpiBytes) / kStageBytes > 8 ? 8 : (222 * 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int kEpiWarpBytes = EPI ? (BN / 4) * 32 * 2 : 2048;   // per-warp staging tile
+  static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kBudget = 227 * 1024 - kBarBytes - 1024 - kEpiBytes;   // 1024: manual alignment slack
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kEpiOffset = kStages * kStageBytes;
   static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static constexpr int kTotal = kBarOffset + kBarBytes + 1024;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
+  static_assert(kStageBytes % 1024 == 0, "staging tiles must stay 1024-byte aligned");
   static constexpr int kAccStride = 256;                         // TMEM columns between accumulator stages
   static_assert(kStages >= 3, "pipeline too shallow");
 };
@@ -315,11 +323,131 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmParams& p, uint32_t
   }
 }
 
-template <int BN, int A_MN, int B_MN, int CTA2>
+// ------------------------------------------------------------------------------------------------
+// bf16 epilogue through shared memory + TMA (EPI = 1).
+// Thread = accumulator row (tcgen05.ld 32x32b); every 16-column chunk is packed to 32 bytes and written into the warp's
+// [32 x W] bf16 tile with the TMA swizzle (W = 64: 128-byte rows, SWIZZLE_128B; W = 32: 64-byte rows, SWIZZLE_64B), which
+// makes the 16-byte st.shared of a quarter-warp hit 32 different banks.  One elected lane then issues a single
+// cp.async.bulk.tensor store for the tile: the LSU sees no row-scattered global access at all (ncu r01: the
+// 32-sectors-per-request st.global / ld.global of the register-direct form bounded the K = 768 GEMMs with two bf16
+// streams).  The aux operand (pre-activation for GELU', ReLU mask) arrives in the SAME tile by TMA load, issued as soon
+// as the previous tile's store has drained the buffer, i.e. a whole MMA main loop ahead of its use; each thread reads
+// its own row chunk and overwrites it in place with the result.  Two outputs (fc1 forward: pre-activation copy +
+// GELU) take two passes over the TMEM accumulator through the one buffer.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+template <int W>
+__device__ __forceinline__ uint32_t stg_off(int lane, int unit16) {
+  if constexpr (W == 64) return (uint32_t)lane * 128u + (uint32_t)((unit16 ^ (lane & 7)) << 4);
+  else return (uint32_t)lane * 64u + (uint32_t)((unit16 ^ ((lane >> 1) & 3)) << 4);
+}
+
+template <int kChunks>
+__device__ __forceinline__ void epilogue_tile_bf16_tma(const GemmParams& p, const CUtensorMap* tm_out,
+                                                       const CUtensorMap* tm_out2, uint8_t* stg, uint64_t* aux_bar,
+                                                       uint32_t aux_phase, uint32_t tmem_addr, uint64_t* tfull,
+                                                       uint32_t tfull_phase, int row0, int col0, bool first_split,
+                                                       int lane) {
+  constexpr int W = kChunks * 16;
+  const bool add_bias = p.bias != nullptr && first_split;
+  const int npass = p.out2 != nullptr ? 2 : 1;
+  u32x8 bs[2][2];
+  auto prefetch = [&](int c, int buf) {
+    const int n = col0 + c * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bs[buf][0].v[j] = 0u; bs[buf][1].v[j] = 0u; }
+    if (add_bias && n < p.N) {
+      bs[buf][0] = ld_global_nc_256(p.bias + n);
+      bs[buf][1] = ld_global_nc_256(p.bias + n + 8);
+    }
+  };
+  prefetch(0, 0);
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  if (p.aux_mode != 0) mbar_wait(aux_bar, aux_phase);
+  uint32_t v[16];
+  int g = 0;   // running chunk counter over the passes (bias double buffer)
+  for (int pass = 0; pass < npass; ++pass) {
+    const bool final_pass = pass == npass - 1;
+    tmem_ld16(tmem_addr, v);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c, ++g) {
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (c + 1 < kChunks) tmem_ld16(tmem_addr + (c + 1) * 16, v);
+      if (c + 1 < kChunks || !final_pass) prefetch((c + 1) % kChunks, (g + 1) & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] += __uint_as_float(bs[g & 1][0].v[j]);
+        f[8 + j] += __uint_as_float(bs[g & 1][1].v[j]);
+      }
+      uint8_t* s0 = stg + stg_off<W>(lane, 2 * c);
+      uint8_t* s1 = stg + stg_off<W>(lane, 2 * c + 1);
+      if (final_pass) {
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (p.aux_mode != 0) {
+          const uint4 a0 = *reinterpret_cast<const uint4*>(s0);
+          const uint4 a1 = *reinterpret_cast<const uint4*>(s1);
+          const uint32_t ax[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          if (p.aux_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 x = unpack_bf16(ax[j]);
+              f[2 * j] *= gelu_erf_grad(x.x);
+              f[2 * j + 1] *= gelu_erf_grad(x.y);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 x = unpack_bf16(ax[j]);
+              f[2 * j] = x.x > 0.0f ? f[2 * j] : 0.0f;
+              f[2 * j + 1] = x.y > 0.0f ? f[2 * j + 1] : 0.0f;
+            }
+          }
+        }
+      }
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+      if (c == 0 && p.aux_mode == 0) {
+        // the previous store out of this buffer must have finished READING it (with aux, the lane that re-filled the
+        // buffer already waited for that)
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
+      *reinterpret_cast<uint4*>(s0) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(s1) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0 && row0 < p.M && col0 < p.N) {
+      tma_store_2d(final_pass ? tm_out : tm_out2, stg, col0, row0);
+      bulk_commit();
+    }
+  }
+}
+
+template <int BN, int A_MN, int B_MN, int CTA2, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const GemmParams p) {
-  using L = Cfg<BN, CTA2>;
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+            const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p) {
+  using L = Cfg<BN, CTA2, EPI>;
   constexpr int kStages = L::kStages;
   constexpr int kNCta = CTA2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -328,7 +456,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;           // one per epilogue warp (EPI = 1 with an aux operand)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -339,6 +468,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (EPI) {
+      tma_prefetch_desc(&tmap_out);
+      if (p.out2 != nullptr) tma_prefetch_desc(&tmap_out2);
+      if (p.aux_mode != 0) tma_prefetch_desc(&tmap_aux);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -348,6 +482,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps * kNCta);
+    }
+    if (EPI) {
+      for (int i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -465,17 +602,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int slice = ew >> 2;            // which quarter of the BN columns
     constexpr int kColsPerWarp = BN / 4;
     constexpr int kChunks = kColsPerWarp / 16;
-    uint8_t* stg = smem + L::kEpiOffset + ew * 2048;
+    uint8_t* stg = smem + L::kEpiOffset + ew * L::kEpiWarpBytes;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t aux_phase = 0;
+    auto tile_origin = [&](int w, int& row0, int& col0) {
+      const int t = w % tiles;
+      const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      row0 = tm * (BM * kNCta) + rank * BM + quad * 32;
+      col0 = tn * BN + slice * kColsPerWarp;
+    };
+    auto load_aux = [&](int w) {   // lane 0: aux tile of work item w -> this warp's staging buffer
+      int r0, c0;
+      tile_origin(w, r0, c0);
+      mbar_expect_tx(&aux_bar[ew], L::kEpiWarpBytes);
+      tma_load_2d(stg, &tmap_aux, &aux_bar[ew], c0, r0);
+    };
+    if (EPI && p.aux_mode != 0 && unit < total_work && lane == 0) load_aux(unit);
     for (int w = unit; w < total_work; w += nunits) {
       const int split = w / tiles;
-      const int t = w - split * tiles;
-      const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-      const int row0 = tm * (BM * kNCta) + rank * BM + quad * 32;
-      const int col0 = tn * BN + slice * kColsPerWarp;
+      int row0, col0;
+      tile_origin(w, row0, col0);
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + slice * kColsPerWarp);
-      if (p.out_f32)
+      if constexpr (EPI != 0)
+        epilogue_tile_bf16_tma<kChunks>(p, &tmap_out, &tmap_out2, stg, &aux_bar[ew], aux_phase, taddr, &tfull_bar[acc],
+                                        acc_phase, row0, col0, split == 0, lane);
+      else if (p.out_f32)
         epilogue_tile_f32<kChunks>(p, stg, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
       else
         epilogue_tile_bf16<kChunks>(p, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
@@ -485,8 +637,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (CTA2 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0);
         else mbar_arrive_relaxed(&tempty_bar[acc]);
       }
+      if (EPI && p.aux_mode != 0) {
+        aux_phase ^= 1;
+        if (lane == 0 && w + nunits < total_work) {
+          bulk_wait_read0();          // the store issued above has drained the buffer
+          load_aux(w + nunits);       // lands while the MMA warp works on the next tile
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI && lane == 0) bulk_wait_read0();   // shared memory must outlive the last store's read
   }
 
   tc_fence_before();
@@ -499,10 +659,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int A_MN, int B_MN, int CTA2>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
-  auto kfn = gemm_kernel<BN, A_MN, B_MN, CTA2>;
-  using L = Cfg<BN, CTA2>;
+struct OutMaps {
+  CUtensorMap out, out2, aux;
+};
+
+template <int BN, int A_MN, int B_MN, int CTA2, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om, const GemmParams& p, int grid,
+                  cudaStream_t st) {
+  auto kfn = gemm_kernel<BN, A_MN, B_MN, CTA2, EPI>;
+  using L = Cfg<BN, CTA2, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -520,19 +685,26 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, ta, tb, p));
+  VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, ta, tb, om.out, om.out2, om.aux, p));
   return 0;
 }
 
-template <int BN, int CTA2>
-static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                        cudaStream_t st) {
+template <int BN, int CTA2, int EPI>
+static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om,
+                        const GemmParams& p, int grid, cudaStream_t st) {
   switch ((a_mn ? 2 : 0) | (b_mn ? 1 : 0)) {
-    case 0: return launch<BN, 0, 0, CTA2>(ta, tb, p, grid, st);
-    case 1: return launch<BN, 0, 1, CTA2>(ta, tb, p, grid, st);
-    case 2: return launch<BN, 1, 0, CTA2>(ta, tb, p, grid, st);
-    default: return launch<BN, 1, 1, CTA2>(ta, tb, p, grid, st);
+    case 0: return launch<BN, 0, 0, CTA2, EPI>(ta, tb, om, p, grid, st);
+    case 1: return launch<BN, 0, 1, CTA2, EPI>(ta, tb, om, p, grid, st);
+    case 2: return launch<BN, 1, 0, CTA2, EPI>(ta, tb, om, p, grid, st);
+    default: return launch<BN, 1, 1, CTA2, EPI>(ta, tb, om, p, grid, st);
   }
+}
+
+template <int BN, int CTA2>
+static int launch_epi(int epi, int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om,
+                      const GemmParams& p, int grid, cudaStream_t st) {
+  if (epi) return launch_major<BN, CTA2, 1>(a_mn, b_mn, ta, tb, om, p, grid, st);
+  return launch_major<BN, CTA2, 0>(a_mn, b_mn, ta, tb, om, p, grid, st);
 }
 
 struct TileChoice {
@@ -541,12 +713,14 @@ struct TileChoice {
 
 // Cost model: a 256xBN pair tile (cta_group::2) and a 128xBN single-CTA tile take about the same time per k-block
 // (the single CTA runs at half the tensor rate), so cost ~ waves * BN * k-blocks-per-work-item.
-static TileChoice choose_tiles(int M, int N, int kblocks, int nsm, bool allow_split, int forced_split, int forced_cfg) {
+static TileChoice choose_tiles(int M, int N, int kblocks, int nsm, bool allow_split, int forced_split, int forced_cfg,
+                               bool allow_192) {
   TileChoice best{0, 256, 1};
   double best_cost = 1e30;
   const int cand[5][2] = {{1, 256}, {1, 192}, {1, 128}, {0, 256}, {0, 128}};
   for (int c = 0; c < 5; ++c) {
     if (forced_cfg >= 0 && c != forced_cfg) continue;
+    if (forced_cfg < 0 && !allow_192 && cand[c][1] == 192) continue;
     const int cta2 = cand[c][0], bn = cand[c][1];
     if (bn > 128 && N <= 128 && forced_cfg < 0) continue;
     const int tm = (M + (cta2 ? 255 : 127)) / (cta2 ? 256 : 128);
@@ -624,7 +798,16 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
           over[i][4] == (d->b_mn_major != 0) && over[i][5] >= 1 && over[i][5] <= 5)
         forced_cfg = over[i][5] - 1;
   }
-  TileChoice tc = choose_tiles(d->M, d->N, p.kblocks, nsm, d->accumulate != 0, d->split_k, forced_cfg);
+  // bf16 outputs leave through shared memory + TMA stores (EPI = 1) on the 256- and 128-column tiles; VS_GEMM_EPI=direct
+  // keeps the register-direct stores (A/B comparisons), VS_GEMM_EPI=tma is the default
+  static int epi_env = -1;
+  if (epi_env < 0) {
+    const char* e = getenv("VS_GEMM_EPI");
+    epi_env = (e && strcmp(e, "direct") == 0) ? 0 : 1;
+  }
+  const bool want_tma = epi_env == 1 && d->out_dtype == 0;
+  TileChoice tc = choose_tiles(d->M, d->N, p.kblocks, nsm, d->accumulate != 0, d->split_k, forced_cfg, !want_tma);
+  const int epi = (want_tma && tc.bn != 192) ? 1 : 0;
   int splits = tc.splits;
   if (splits > p.kblocks) splits = p.kblocks;
   // every split must own at least one k-block
@@ -665,16 +848,37 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
     rc = make_tmap_bf16(&tb, d->B, 2, dims, strides, box);
     if (rc) return rc;
   }
+  OutMaps om;
+  om.out = ta; om.out2 = ta; om.aux = ta;   // placeholders (never dereferenced) unless EPI = 1
+  if (epi) {
+    // one [32 rows x BN/4 columns] box per epilogue warp; 128-byte rows (BN = 256) or 64-byte rows (BN = 128)
+    uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M}, strides[1];
+    uint32_t box[2] = {(uint32_t)(BN / 4), 32u};
+    const int sw = BN == 256 ? 128 : 64;
+    strides[0] = (uint64_t)d->ldo * 2;
+    int rc = make_tmap_bf16_sw(&om.out, d->out, 2, dims, strides, box, sw);
+    if (rc) return rc;
+    if (d->out2) {
+      strides[0] = (uint64_t)d->ldo2 * 2;
+      rc = make_tmap_bf16_sw(&om.out2, d->out2, 2, dims, strides, box, sw);
+      if (rc) return rc;
+    }
+    if (d->aux_mode) {
+      strides[0] = (uint64_t)d->ldaux * 2;
+      rc = make_tmap_bf16_sw(&om.aux, d->aux, 2, dims, strides, box, sw);
+      if (rc) return rc;
+    }
+  }
   const int total = p.tiles_m * p.tiles_n * splits;
   cudaStream_t st = (cudaStream_t)stream;
   if (tc.cta2) {
     const int pairs = nsm / 2;
     const int grid = 2 * (total < pairs ? total : pairs);
-    if (BN == 256) return launch_major<256, 1>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
-    if (BN == 192) return launch_major<192, 1>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
-    return launch_major<128, 1>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
+    if (BN == 256) return launch_epi<256, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
+    if (BN == 192) return launch_major<192, 1, 0>(d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
+    return launch_epi<128, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
   }
   const int grid = total < nsm ? total : nsm;
-  if (BN == 256) return launch_major<256, 0>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
-  return launch_major<128, 0>(d->a_mn_major, d->b_mn_major, ta, tb, p, grid, st);
+  if (BN == 256) return launch_epi<256, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
+  return launch_epi<128, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
 }

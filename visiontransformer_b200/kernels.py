@@ -286,13 +286,15 @@ def sdf_targets(mask):
     return ext, inn
 
 
-def upsample_ce(low, labels, loss_sum, dlow):
+def upsample_ce(low, labels, loss_sum, dlow, size):
+    """labels int64 or uint8 [B, LH, LW]; LH x LW != size x size = nearest-resized on the fly (CE/classes.py:273-274)."""
     require_cuda(low, "upsample_ce")
     B, Cn, g, _ = low.shape
-    S = labels.shape[-1]
-    assert labels.dtype == torch.int64 and labels.is_contiguous() and low.is_contiguous()
+    assert labels.dtype in (torch.int64, torch.uint8) and labels.is_contiguous() and low.is_contiguous()
+    assert labels.dim() == 3 and labels.shape[0] == B
     _count(1)
-    check(_lib.load().vs_upsample_ce(ptr(low), ptr(labels), ptr(loss_sum), ptr(dlow), B, Cn, g, S, stream()),
+    check(_lib.load().vs_upsample_ce(ptr(low), ptr(labels), 0 if labels.dtype == torch.int64 else 1, labels.shape[1],
+                                     labels.shape[2], ptr(loss_sum), ptr(dlow), B, Cn, g, size, stream()),
           "vs_upsample_ce")
 
 

@@ -20,12 +20,16 @@ class _UpsampleCE(torch.autograd.Function):
     def forward(ctx, low, labels, size):
         low = low.contiguous()
         labels = labels.contiguous()
-        if labels.shape[-1] != size or labels.shape[-2] != size:
-            raise ValueError(f"labels must be [B,{size},{size}], got {tuple(labels.shape)}")
+        if labels.dim() == 4 and labels.shape[1] == 1:
+            labels = labels[:, 0]
+        if labels.dim() != 3 or labels.shape[0] != low.shape[0]:
+            raise ValueError(f"labels must be [B,H,W], got {tuple(labels.shape)}")
+        if labels.dtype not in (torch.int64, torch.uint8):
+            labels = labels.long()
         loss_sum = torch.zeros(2, device=low.device, dtype=F32)
         need = ctx.needs_input_grad[0]
         dlow = torch.zeros_like(low) if need else None
-        K.upsample_ce(low, labels, loss_sum, dlow)
+        K.upsample_ce(low, labels, loss_sum, dlow, size)
         ctx.save_for_backward(dlow if need else torch.empty(0), loss_sum)
         return loss_sum[0] / loss_sum[1]
 
@@ -36,7 +40,9 @@ class _UpsampleCE(torch.autograd.Function):
 
 
 def upsample_cross_entropy(low: torch.Tensor, labels: torch.Tensor, size: int) -> torch.Tensor:
-    """mean over non-ignored pixels of -log_softmax(bilinear_up(low))[label]; labels int64 [B,S,S]."""
+    """mean over non-ignored pixels of -log_softmax(bilinear_up(low))[label].  labels int64 (or uint8) [B,H,W]; when
+    H x W differs from size x size the kernel reads them through the legacy-'nearest' index map of
+    F.interpolate(y.float(), size, mode='nearest') — LightningViTModel._resize_target without the three extra passes."""
     K.require_cuda(low, "upsample_cross_entropy")
     return _UpsampleCE.apply(low, labels, size)
 
