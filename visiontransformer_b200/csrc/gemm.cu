@@ -48,6 +48,7 @@ struct GemmParams {
   long long ldr;
   int row_tokens;
   DropCfg drop;  // hidden-state dropout applied to (acc + bias) before the residual add (fp32 outputs only)
+  int dynamic;   // 1: tiles are handed out by cluster launch control (grid = one cluster per work item)
 };
 
 // EPI = 0: register-direct / smem-transposed epilogues (fp32 outputs, accumulation, BN = 192).
@@ -131,6 +132,78 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(leader_bar)
       : "memory");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Dynamic tile scheduling by cluster launch control (sm_100 CLC).  The kernel is launched with ONE cluster per work
+// item; the clusters that get an SM pair keep running and "cancel" clusters that have not started yet, taking over
+// their work item.  Unlike a persistent grid with a static tile assignment, this adapts to how many SMs the kernel
+// actually received: when NCCL's all-reduce CTAs of the data-parallel step hold some SMs, a static 148-CTA grid runs
+// its displaced CTAs as a second wave (SCALE_r01: GEMM roofline fraction 0.61 -> 0.53 at 8 GPUs); here the remaining
+// SMs simply take more tiles.
+//   scheduler (warp 3 of the leader CTA): try_cancel -> 16-byte response multicast into the same smem slot of every CTA of
+//   the cluster, signalled on each CTA's sched_full[slot]; consumers (producer / MMA / epilogue warps of both CTAs) decode
+//   it and release the slot on the leader's sched_empty[slot].
+// ------------------------------------------------------------------------------------------------
+constexpr int kSched = 4;
+struct SchedSmem {
+  uint4 resp[kSched];
+  uint64_t full[kSched];
+  uint64_t empty[kSched];
+};
+__device__ __forceinline__ void mbar_expect_tx_remote(uint64_t* bar, uint32_t rank, uint32_t bytes) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(bytes)
+               : "memory");
+}
+template <int CTA2>
+__device__ __forceinline__ void clc_try_cancel(uint4* resp, uint64_t* bar) {
+  if (CTA2)
+    asm volatile(
+        "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+        "[%0], [%1];" ::"r"(smem_u32(resp)), "r"(smem_u32(bar))
+        : "memory");
+  else
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 ::"r"(smem_u32(resp)), "r"(smem_u32(bar))
+                 : "memory");
+}
+// -> first CTA id (x) of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_decode(const uint4* resp) {
+  uint32_t x = 0, valid = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, r;\n\t}\n"
+      : "+r"(x), "=r"(valid)
+      : "r"(smem_u32(resp))
+      : "memory");
+  return valid ? (int)x : -1;
+}
+// iteration state of one consumer warp over the work items of its cluster
+template <int CTA2>
+struct TileIter {
+  SchedSmem* ss;
+  int it, step, total;
+  uint32_t rank;
+  bool dynamic;
+  __device__ __forceinline__ int next(int w, int lane) {
+    if (!dynamic) return (w + step < total) ? w + step : -1;
+    const int slot = it & (kSched - 1);
+    mbar_wait(&ss->full[slot], (uint32_t)(it / kSched) & 1u);
+    const int x = clc_decode(&ss->resp[slot]);
+    fence_proxy_async_smem();   // the slot is re-written by the async proxy after the release below
+    __syncwarp();
+    if (lane == 0) {
+      if (CTA2 && rank != 0) mbar_arrive_remote(&ss->empty[slot], 0);
+      else mbar_arrive_relaxed(&ss->empty[slot]);
+    }
+    ++it;
+    return x < 0 ? -1 : x / (CTA2 ? 2 : 1);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue math + I/O for 4 consecutive columns of one output row.  The epilogue warps transpose each 32x32
@@ -458,6 +531,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* aux_bar = tempty_bar + 2;           // one per epilogue warp (EPI = 1 with an aux operand)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+  SchedSmem* ss = reinterpret_cast<SchedSmem*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -486,6 +560,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (EPI) {
       for (int i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     }
+    for (int i = 0; i < kSched; ++i) {
+      mbar_init(&ss->full[i], 1);
+      // consumers per cluster: leader = producer + MMA + epilogue warps + the scheduler itself; peer = producer + epilogue
+      mbar_init(&ss->empty[i], (kEpiWarps + 3) + (CTA2 ? kEpiWarps + 1 : 0));
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -503,6 +582,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
   const int unit = blockIdx.x / kNCta;
   const int nunits = gridDim.x / kNCta;
+  TileIter<CTA2> ti{ss, 0, nunits, total_work, rank, p.dynamic != 0};
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (each CTA loads its A rows and its B half)
@@ -510,7 +590,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr uint32_t kBytesB = B_MN ? L::kBBoxes * 64 * BK * 2 : L::kBNH * BK * 2;
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = unit; w < total_work; w += nunits) {
+    for (int w = unit; w >= 0; w = ti.next(w, lane)) {
       const int split = w / tiles;
       const int t = w - split * tiles;
       const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
@@ -559,7 +639,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = unit; w < total_work; w += nunits) {
+      for (int w = unit; w >= 0; w = ti.next(w, lane)) {
         const int split = w / tiles;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + kb_per_split);
@@ -595,6 +675,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------ tile scheduler (leader CTA, one lane): cluster launch control
+    if (leader && p.dynamic && lane == 0) {
+      for (int it = 0;; ++it) {
+        const int slot = it & (kSched - 1);
+        if (it >= kSched) mbar_wait(&ss->empty[slot], (uint32_t)(it / kSched - 1) & 1u);
+        mbar_expect_tx(&ss->full[slot], 16);
+        if (CTA2) mbar_expect_tx_remote(&ss->full[slot], 1, 16);
+        clc_try_cancel<CTA2>(&ss->resp[slot], &ss->full[slot]);
+        mbar_wait(&ss->full[slot], (uint32_t)(it / kSched) & 1u);
+        const int x = clc_decode(&ss->resp[slot]);
+        fence_proxy_async_smem();
+        mbar_arrive_relaxed(&ss->empty[slot]);
+        if (x < 0) break;   // nothing left to cancel: every consumer reads the same "no more work" response
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue (this CTA's 128 rows of the tile)
     const int ew = warp - 4;
@@ -618,8 +714,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_expect_tx(&aux_bar[ew], L::kEpiWarpBytes);
       tma_load_2d(stg, &tmap_aux, &aux_bar[ew], c0, r0);
     };
-    if (EPI && p.aux_mode != 0 && unit < total_work && lane == 0) load_aux(unit);
-    for (int w = unit; w < total_work; w += nunits) {
+    if (EPI && p.aux_mode != 0 && lane == 0) load_aux(unit);
+    int w_next = ti.next(unit, lane);   // one work item ahead: the aux tile of the next item is prefetched
+    for (int w = unit; w >= 0; w = w_next, w_next = (w >= 0 ? ti.next(w, lane) : -1)) {
       const int split = w / tiles;
       int row0, col0;
       tile_origin(w, row0, col0);
@@ -639,9 +736,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (EPI && p.aux_mode != 0) {
         aux_phase ^= 1;
-        if (lane == 0 && w + nunits < total_work) {
+        if (lane == 0 && w_next >= 0) {
           bulk_wait_read0();          // the store issued above has drained the buffer
-          load_aux(w + nunits);       // lands while the MMA warp works on the next tile
+          load_aux(w_next);           // lands while the MMA warp works on the next tile
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -871,14 +968,22 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   }
   const int total = p.tiles_m * p.tiles_n * splits;
   cudaStream_t st = (cudaStream_t)stream;
+  // VS_GEMM_SCHED=clc: one cluster per work item, tiles handed out by cluster launch control (adapts to the SMs the
+  // kernel actually gets, e.g. next to NCCL's CTAs); VS_GEMM_SCHED=static: persistent grid, fixed round-robin assignment
+  static int sched_env = -1;
+  if (sched_env < 0) {
+    const char* e = getenv("VS_GEMM_SCHED");
+    sched_env = (e && strcmp(e, "clc") == 0) ? 1 : 0;
+  }
+  p.dynamic = sched_env;
   if (tc.cta2) {
     const int pairs = nsm / 2;
-    const int grid = 2 * (total < pairs ? total : pairs);
+    const int grid = p.dynamic ? 2 * total : 2 * (total < pairs ? total : pairs);
     if (BN == 256) return launch_epi<256, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     if (BN == 192) return launch_major<192, 1, 0>(d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     return launch_epi<128, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
   }
-  const int grid = total < nsm ? total : nsm;
+  const int grid = p.dynamic ? total : (total < nsm ? total : nsm);
   if (BN == 256) return launch_epi<256, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
   return launch_epi<128, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
 }
