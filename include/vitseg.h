@@ -92,6 +92,11 @@ int vs_gemm_bf16(const vs_gemm_desc* d, void* stream);
 /* column sums of a bf16 [M, N] matrix into fp32 out[N] (bias gradients; autograd of nn.Linear bias).
  * accumulate != 0 adds to out. */
 int vs_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate, void* stream);
+/* same, but the first nf columns of the matrix are still fp32 in x_f32 [M, ldf] (the dQ accumulator of the attention
+ * backward): they are rounded to bf16, STORED into x[:, :nf] and summed from the rounded values — one pass instead of a
+ * cast pass plus a column-sum pass. */
+int vs_colsum_cast_bf16(void* x, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate, const float* x_f32,
+                        int64_t ldf, int32_t nf, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (TF:325-326,333,340,416,455; eps 1e-12), fp32 residual stream in, bf16 (and/or fp32) out.
@@ -176,6 +181,22 @@ int vs_colorize_mask(const uint8_t* mask, const uint8_t* palette, uint8_t* rgb, 
  *   model/CE/datasetTestViTmodel.py:188-217 are functions of these counts (visiontransformer_b200/metrics.py). */
 int vs_upsample_argmax_stats(const float* low, const int64_t* labels, uint8_t* mask, int32_t* counts, int32_t B,
                              int32_t C, int32_t g, int32_t S, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Worker-side pre-processing: Pillow's Image.resize(size, BILINEAR) — what
+ * transforms.Resize((224, 224)) does to the PIL image at model/CE/testViTModel.py:92-97 — followed by ToTensor, on
+ * planar uint8 [C,H,W] device images (the layout nvJPEG delivers).  Two passes as in libImaging/Resample.c: horizontal
+ * into a rounded uint8 intermediate [C,H,Wout], then vertical; 22-bit fixed-point weights.  bounds [out*2] = (first
+ * source index, tap count) and coef [out*ksize] int32 per output coordinate come from the host (precompute_coeffs /
+ * normalize_coeffs_8bpc restated in visiontransformer_b200/worker.py).  Bit-identical to Pillow for the same pixels.
+ *   vs_resample_v_u8 writes dst_f32 = value * scale (ToTensor: scale = 1/255) and/or dst_u8 (either may be NULL).
+ *   vs_u8_to_f32: ToTensor alone (no resize needed).
+ * ------------------------------------------------------------------------------------------------ */
+int vs_resample_h_u8(const uint8_t* src, int64_t row_stride, int64_t plane_stride, int32_t C, int32_t H, int32_t W,
+                     const int32_t* bounds, const int32_t* coef, int32_t ksize, int32_t Wout, uint8_t* dst, void* stream);
+int vs_resample_v_u8(const uint8_t* src, int32_t C, int32_t H, int32_t Wout, const int32_t* bounds, const int32_t* coef,
+                     int32_t ksize, int32_t Hout, float* dst_f32, float scale, uint8_t* dst_u8, void* stream);
+int vs_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused upsample + cross-entropy (model/CE/classes.py:276-285: F.interpolate -> nn.CrossEntropyLoss, mean over

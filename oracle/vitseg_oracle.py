@@ -275,21 +275,23 @@ def learnable_labels(x, num_classes, patch=16):
     return F.interpolate(lab, size=x.shape[-2:], mode="nearest").squeeze(1).long()
 
 
-def curve_task(name: str, B: int = 2, S: int = 224, num_classes: int = 17):
-    """fixed batches for the 200-step loss-curve parity run (tests/golden/vitb16_curve.pt).
-      'regions': 32-pixel blocks, each of one class, coloured from a fixed palette plus 20 % pixel noise; 25 % of the
-                 label pixels are replaced by uniformly random classes, so the loss falls smoothly from ln(17) towards
-                 an irreducible floor near 1.2 instead of collapsing to 0 (where a relative gap is meaningless);
+def curve_task(name: str = "regions", B: int = 2, S: int = 224, num_classes: int = 17, block: int = 32,
+               noise: float = 0.5, contrast: float = 0.8):
+    """fixed batch for the 200-step loss-curve parity run (tests/golden/vitb16_curve.pt).
+      'regions': block x block pixel cells, each of one class, coloured from a fixed palette (scaled by `contrast`) plus
+                 uniform pixel noise; a fraction `noise` of the label pixels is replaced by uniformly random classes, so
+                 the loss falls smoothly from ln(17) towards an irreducible floor instead of collapsing to 0 (where a
+                 relative gap is meaningless);
       'brightness': the learnable_labels task of the 60-step test."""
     g = torch.Generator().manual_seed(77)
     if name == "regions":
         pal = torch.rand(num_classes, 3, generator=g)
-        z = torch.randint(0, num_classes, (B, S // 32, S // 32), generator=g)
-        z = z.repeat_interleave(32, 1).repeat_interleave(32, 2)
-        x = pal[z].permute(0, 3, 1, 2) * 0.8 + 0.2 * torch.rand(B, 3, S, S, generator=g)
+        z = torch.randint(0, num_classes, (B, S // block, S // block), generator=g)
+        z = z.repeat_interleave(block, 1).repeat_interleave(block, 2)
+        x = pal[z].permute(0, 3, 1, 2) * contrast + (1.0 - contrast) * torch.rand(B, 3, S, S, generator=g)
         x = x.to(torch.bfloat16).to(torch.float32)
-        noise = torch.rand(B, S, S, generator=g) < 0.25
-        y = torch.where(noise, torch.randint(0, num_classes, (B, S, S), generator=g), z)
+        flip = torch.rand(B, S, S, generator=g) < noise
+        y = torch.where(flip, torch.randint(0, num_classes, (B, S, S), generator=g), z)
         return x, y
     x = synthetic_images(B, S, seed=32)
     return x, learnable_labels(x, num_classes)

@@ -193,7 +193,7 @@ def test_paed_trainer_helper_methods_and_test_step():
     assert abs(la.item() - lr_.item()) < 1e-5 * abs(lr_.item()) + 1e-7
     la.backward()
     lr_.backward()
-    assert ((pa.grad.cpu() - pr.grad).abs().max() / pr.grad.abs().max()).item() < 1e-4
+    assert ((pa.grad.cpu() - pr.grad).abs().max() / pr.grad.abs().max()).item() < 5e-4   # torch CUDA vs torch CPU, fp32
     # a subclass written like the reference's own step (dense tensors + the helper methods) reproduces the fused loss
     logits = m(x)
     p = torch.sigmoid(logits)

@@ -38,6 +38,7 @@ _SIGS = {
     "vs_device_sm_count": [],
     "vs_gemm_bf16": [C.POINTER(GemmDesc), c_void_p],
     "vs_colsum_bf16": [c_void_p, c_i64, c_int, c_int, c_void_p, c_int, c_void_p],
+    "vs_colsum_cast_bf16": [c_void_p, c_i64, c_int, c_int, c_void_p, c_int, c_void_p, c_i64, c_int, c_void_p],
     "vs_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p],
     "vs_layernorm_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
@@ -60,6 +61,10 @@ _SIGS = {
     "vs_upsample_argmax": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_upsample_argmax_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vs_colorize_mask": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p],
+    "vs_resample_h_u8": [c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "vs_resample_v_u8": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p,
+                         c_void_p],
+    "vs_u8_to_f32": [c_void_p, c_void_p, c_i64, c_float, c_void_p],
     "vs_sdf_workspace_bytes": [c_int, c_int],
     "vs_sdf_targets": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "vs_upsample_ce": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
                 const DropCfg drop) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::kBar);
@@ -332,6 +334,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                       __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
                       const DropCfg drop) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdShortSmem::kBar);
@@ -540,6 +544,8 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                   float* __restrict__ delta, float* __restrict__ dq_accum, int B, int N, int H) {
+  pdl_wait();
+  pdl_trigger();
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // also clears the dQ accumulators of this warp's 32 rows (layout [B, N, H, 64] = row * 64; 8 KB contiguous per warp,
   // 512 B per store instruction): saves the separate memset launch
@@ -593,6 +599,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
                 const __grid_constant__ CUtensorMap tmap_do, const float* __restrict__ lse,
                 const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_accum,
                 int B, int N, int H, float scale, const DropCfg drop) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBar);
@@ -920,8 +928,7 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
     DropCfg dcs;
     if (int rc2 = make_drop(&dcs, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
     dim3 grid_s((N + kBQ - 1) / kBQ, H, B);
-    attn_fwd_short_kernel<<<grid_s, kFwdThreads, AttnFwdShortSmem::kTotal, (cudaStream_t)stream>>>(
-        tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dcs);
+    launch_k(attn_fwd_short_kernel, dim3(grid_s), dim3(kFwdThreads), (size_t)(AttnFwdShortSmem::kTotal), (cudaStream_t)stream, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dcs);
     VS_CHECK_LAUNCH();
     return 0;
   }
@@ -936,8 +943,7 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
-  attn_fwd_kernel<2><<<grid, kFwdThreads, AttnFwdSmem::kTotal, (cudaStream_t)stream>>>(tm, tkv, (__nv_bfloat16*)ctx, lse,
-                                                                                       B, N, H, scale, dc);
+  launch_k(attn_fwd_kernel<2>, dim3(grid), dim3(kFwdThreads), (size_t)(AttnFwdSmem::kTotal), (cudaStream_t)stream, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -971,8 +977,7 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
   {
     const long long rows = (long long)B * N * H;
-    attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)ctx,
-                                                                      (const __nv_bfloat16*)dctx, delta, dq_accum, B, N, H);
+    launch_k(attn_delta_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), (size_t)(0), st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, delta, dq_accum, B, N, H);
     VS_CHECK_LAUNCH();
   }
   const long long items = (long long)B * H * ((N + kKB - 1) / kKB);
@@ -986,8 +991,7 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
   while (g > 1 && gcd(g, nkb) != 1) --g;
   const unsigned grid = (unsigned)g;
-  attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv,
-                                                                  dq_accum, B, N, H, scale, dc);
+  launch_k(attn_bwd_kernel, dim3(grid), dim3(kBwdThreads), (size_t)(AttnBwdSmem::kTotal), st, tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, dq_accum, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }

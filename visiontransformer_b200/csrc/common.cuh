@@ -44,6 +44,38 @@ int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and begins with pdl_wait() — griddepcontrol.wait: block until all
+// prerequisite grids have COMPLETED and their memory is visible — followed by pdl_trigger(), which lets the next
+// kernel of the stream be scheduled while this one is still running.  The next kernel's launch processing and its
+// on-chip prologue (barrier init, TMEM allocation, tensor-map prefetch, placed BEFORE its own pdl_wait) then overlap
+// this kernel's tail instead of forming a ~1-2 us bubble per launch (r01: 297 launches per training step).
+// Correctness rule: a kernel touches global memory only after its own pdl_wait(), and every thread executes it
+// before any early exit — then "B waited for A" holds transitively along the stream (C waits for all of B, all of B
+// waited for all of A).  VS_PDL=0 launches without the attribute (griddepcontrol.* are then no-ops).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------------------------
 // generic device helpers
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

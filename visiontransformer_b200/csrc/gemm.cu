@@ -576,6 +576,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (CTA2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is on-chip prologue (barriers, TMEM, descriptor prefetch) and overlaps the previous kernel's tail
+  // under programmatic dependent launch; no global memory is touched before this point
+  pdl_wait();
+  pdl_trigger();
 
   const int tiles = p.tiles_m * p.tiles_n;
   const int total_work = tiles * p.splits;
@@ -678,17 +682,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 3) {
     // ------------------------------------------------ tile scheduler (leader CTA, one lane): cluster launch control
     if (leader && p.dynamic && lane == 0) {
-      for (int it = 0;; ++it) {
-        const int slot = it & (kSched - 1);
-        if (it >= kSched) mbar_wait(&ss->empty[slot], (uint32_t)(it / kSched - 1) & 1u);
-        mbar_expect_tx(&ss->full[slot], 16);
-        if (CTA2) mbar_expect_tx_remote(&ss->full[slot], 1, 16);
-        clc_try_cancel<CTA2>(&ss->resp[slot], &ss->full[slot]);
-        mbar_wait(&ss->full[slot], (uint32_t)(it / kSched) & 1u);
+      // up to kSched - 1 queries in flight: the answer to a try_cancel takes longer than one short tile
+      int issued = 0, consumed = 0;
+      bool more = true;
+      for (;;) {
+        while (more && issued - consumed < kSched - 1) {
+          const int slot = issued & (kSched - 1);
+          if (issued >= kSched) mbar_wait(&ss->empty[slot], (uint32_t)(issued / kSched - 1) & 1u);
+          mbar_expect_tx(&ss->full[slot], 16);
+          if (CTA2) mbar_expect_tx_remote(&ss->full[slot], 1, 16);
+          clc_try_cancel<CTA2>(&ss->resp[slot], &ss->full[slot]);
+          ++issued;
+        }
+        if (consumed == issued) break;
+        const int slot = consumed & (kSched - 1);
+        mbar_wait(&ss->full[slot], (uint32_t)(consumed / kSched) & 1u);
         const int x = clc_decode(&ss->resp[slot]);
         fence_proxy_async_smem();
         mbar_arrive_relaxed(&ss->empty[slot]);
-        if (x < 0) break;   // nothing left to cancel: every consumer reads the same "no more work" response
+        ++consumed;
+        if (x < 0) more = false;   // nothing left to cancel; the queries still in flight are drained before exit
       }
     }
   } else if (warp >= 4) {
@@ -775,13 +788,15 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& o
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, ta, tb, om.out, om.out2, om.aux, p));
   return 0;
 }

@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               int M, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float* __restrict__ mean_out,
               float* __restrict__ rstd_out) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -80,6 +82,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const f
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dx_in, int M,
               float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dbias, const DropCfg drop, const int stages) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int D = NV * 128;
   constexpr int kDyRow = D * (DY_F32 ? 4 : 2);
   constexpr int kStageBytes = kLnbRows * (2 * D * 4 + kDyRow);   // x | dx_in | dy
@@ -234,7 +238,7 @@ extern "C" int vs_layernorm_fwd(const float* x, const float* gamma, const float*
   const int grid = (M + 7) / 8;
   __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
   switch (D / 128) {
-#define VS_LN_CASE(NV) case NV: ln_fwd_kernel<NV><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, yb, y_f32, mean, rstd); break;
+#define VS_LN_CASE(NV) case NV: launch_k(ln_fwd_kernel<NV>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, eps, M, yb, y_f32, mean, rstd); break;
     VS_LN_CASE(1) VS_LN_CASE(2) VS_LN_CASE(3) VS_LN_CASE(4) VS_LN_CASE(5) VS_LN_CASE(6) VS_LN_CASE(7) VS_LN_CASE(8)
 #undef VS_LN_CASE
   }
@@ -279,8 +283,7 @@ extern "C" int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* 
                                          128 + 128 + 1024 * 4 + 200 * 1024));                                        \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    ln_bwd_kernel<NV, F32><<<grid, kLnbThreads, smem_bytes, st>>>(dy, x, gamma, mean, rstd, dx_in, M, dx_out, db,    \
-                                                                   dgamma, dbeta, dbias_colsum, dc, stages);         \
+    launch_k(ln_bwd_kernel<NV, F32>, dim3(grid), dim3(kLnbThreads), (size_t)(smem_bytes), st, dy, x, gamma, mean, rstd, dx_in, M, dx_out, db, dgamma, dbeta, dbias_colsum, dc, stages);         \
   }
 #define VS_LN_CASE(NV)                                                                                               \
   case NV:                                                                                                           \

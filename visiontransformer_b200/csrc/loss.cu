@@ -53,6 +53,8 @@ __device__ __forceinline__ Region region_of(long long rid, int g, int S) {
 // ================================================================================================
 __global__ void __launch_bounds__(256)
 upsample_fwd_kernel(const float* __restrict__ low, float* __restrict__ full, int g, int S, int chunks) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_plane[];
   const long long plane = blockIdx.x / chunks;
   const int chunk = blockIdx.x % chunks;
@@ -83,6 +85,8 @@ upsample_fwd_kernel(const float* __restrict__ low, float* __restrict__ full, int
 // one warp per (plane, region): dlow[plane, cells] += sum over the region's pixels
 __global__ void __launch_bounds__(256)
 upsample_bwd_kernel(const float* __restrict__ dfull, float* __restrict__ dlow, long long planes, int g, int S) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long nreg = planes * (g + 1) * (g + 1);
   const long long rid = (long long)blockIdx.x * 8 + warp;
@@ -143,6 +147,8 @@ static int low_rows_bound(int rows_per, int g, int S) {   // host: upper bound o
 
 __global__ void __launch_bounds__(256)
 upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask, int C, int g, int S, int chunks) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_low_raw[];  // [C][staged rows][g]
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   const float scale = (float)g / (float)S;
@@ -187,6 +193,8 @@ upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask
 __global__ void __launch_bounds__(256)
 colorize_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ palette, uint8_t* __restrict__ rgb,
                 long long n, int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint8_t s_pal[256 * 3];
   for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) s_pal[i] = i < C * 3 ? palette[i] : 0;
   __syncthreads();
@@ -230,6 +238,8 @@ __device__ __forceinline__ void warp_hist_add(int* hist, int key, bool valid) {
 __global__ void __launch_bounds__(256)
 upsample_argmax_stats_kernel(const float* __restrict__ low, const long long* __restrict__ labels,
                              uint8_t* __restrict__ mask, int* __restrict__ counts, int C, int g, int S, int chunks) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_low_raw[];  // [C][staged rows][g]
   __shared__ int s_hist[8][3][kStatMaxClasses];   // per warp: intersection / predicted / target
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
@@ -308,6 +318,8 @@ template <int CMAX, typename LabelT>
 __global__ void __launch_bounds__(CeCfg<CMAX>::kWarps * 32)
 upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ labels, int LH, int LW, float lab_sy,
                    float lab_sx, float* __restrict__ loss_sum, float* __restrict__ dlow, int B, int C, int g, int S) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int kWarps = CeCfg<CMAX>::kWarps;
   constexpr int kPad = CeCfg<CMAX>::kPad;
   constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
@@ -492,6 +504,8 @@ __global__ void __launch_bounds__(256)
 paed_binary_stats_kernel(const float* __restrict__ low, const float* __restrict__ mask, const float* __restrict__ sdf_ext,
                          const float* __restrict__ sdf_int, float* __restrict__ stats,
                          unsigned long long* __restrict__ keys, int B, int g, int S) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_low[kMaxG * kMaxG];
   __shared__ float s_p[(kMaxP + 2) * (kMaxP + 2)];
   __shared__ float s_red[8][6];
@@ -555,6 +569,8 @@ __global__ void __launch_bounds__(256)
 paed_binary_bwd_kernel(const float* __restrict__ low, const float* __restrict__ mask, const float* __restrict__ sdf_ext,
                        const float* __restrict__ sdf_int, const float* __restrict__ coef,
                        const unsigned long long* __restrict__ keys, float* __restrict__ dlow, int B, int g, int S) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_low[kMaxG * kMaxG];
   __shared__ float s_p[(kMaxP + 4) * (kMaxP + 4)];
   __shared__ float s_gx[(kMaxP + 2) * (kMaxP + 2)];
@@ -641,6 +657,8 @@ __global__ void __launch_bounds__(256)
 pm_pixel_kernel(const float* __restrict__ low, const long long* __restrict__ labels, const float* __restrict__ tin,
                 const float* __restrict__ bu, float* __restrict__ out, float* __restrict__ loss_sum, int mode, int C,
                 int g, int S, int chunks) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_low_raw[];  // [C][staged rows][g]
   __shared__ float s_red[8];
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
@@ -733,6 +751,8 @@ constexpr int kBlurPad = 12;    // zero columns on both sides of a staged row (>
 
 __global__ void __launch_bounds__(256)
 blur2d_kernel(const float* __restrict__ in, float* __restrict__ out, int S, int tiles_y) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float s_blur[];
   const int SP = S + 2 * kBlurPad;
   constexpr int R = kBlurTR + 18;
@@ -805,7 +825,7 @@ static int launch_blur2d(const float* in, float* out, long long planes, int S, c
     smem_set = smem;
   }
   VS_CHECK_ARG(planes * tiles_y < (1LL << 31), "PAED blur: too many planes");
-  blur2d_kernel<<<(unsigned)(planes * tiles_y), 256, smem, st>>>(in, out, S, tiles_y);
+  launch_k(blur2d_kernel, dim3((unsigned)(planes * tiles_y)), dim3(256), (size_t)(smem), st, in, out, S, tiles_y);
   return 0;
 }
 
@@ -815,6 +835,8 @@ __global__ void __launch_bounds__(256)
 pmd_elem_kernel(const float* __restrict__ m, const float* __restrict__ p, const float* __restrict__ t,
                 const float* __restrict__ bu, float* __restrict__ out, float* __restrict__ loss_sum, long long n,
                 int mode, int class_penalty) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_red[8];
   float loss = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -875,8 +897,7 @@ extern "C" int vs_upsample_bilinear_fwd(const float* low, float* full, int32_t B
   const long long planes = (long long)B * C;
   int chunks = 1;
   while (planes * chunks < (long long)sm_count() * 4 && chunks < S / 8) chunks *= 2;
-  upsample_fwd_kernel<<<(unsigned)(planes * chunks), 256, g * g * sizeof(float), (cudaStream_t)stream>>>(low, full, g, S,
-                                                                                                        chunks);
+  launch_k(upsample_fwd_kernel, dim3((unsigned)(planes * chunks)), dim3(256), (size_t)(g * g * sizeof(float)), (cudaStream_t)stream, low, full, g, S, chunks);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -889,7 +910,7 @@ extern "C" int vs_upsample_bilinear_bwd(const float* dfull, float* dlow, int32_t
   const long long planes = (long long)B * C;
   VS_CHECK_CUDA(cudaMemsetAsync(dlow, 0, (size_t)planes * g * g * sizeof(float), st));
   const long long nreg = planes * (g + 1) * (g + 1);
-  upsample_bwd_kernel<<<(unsigned)((nreg + 7) / 8), 256, 0, st>>>(dfull, dlow, planes, g, S);
+  launch_k(upsample_bwd_kernel, dim3((unsigned)((nreg + 7) / 8)), dim3(256), (size_t)(0), st, dfull, dlow, planes, g, S);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -927,7 +948,7 @@ extern "C" int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, in
     VS_CHECK_CUDA(cudaFuncSetAttribute(upsample_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  upsample_argmax_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(low, mask, C, g, S, chunks);
+  launch_k(upsample_argmax_kernel, dim3(B * chunks), dim3(256), (size_t)(smem), (cudaStream_t)stream, low, mask, C, g, S, chunks);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -941,7 +962,7 @@ extern "C" int vs_colorize_mask(const uint8_t* mask, const uint8_t* palette, uin
   long long nb = (n / 4 + 255) / 256;
   if (nb > (long long)nsm * 16) nb = (long long)nsm * 16;
   if (nb < 1) nb = 1;
-  colorize_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(mask, palette, rgb, n, C);
+  launch_k(colorize_kernel, dim3((unsigned)nb), dim3(256), (size_t)(0), (cudaStream_t)stream, mask, palette, rgb, n, C);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -963,8 +984,7 @@ extern "C" int vs_upsample_argmax_stats(const float* low, const int64_t* labels,
   cudaStream_t st = (cudaStream_t)stream;
   const int NC = C == 1 ? 2 : C;
   VS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * NC * 3 * sizeof(int32_t), st));
-  upsample_argmax_stats_kernel<<<B * chunks, 256, smem, st>>>(low, (const long long*)labels, mask, counts, C, g, S,
-                                                              chunks);
+  launch_k(upsample_argmax_stats_kernel, dim3(B * chunks), dim3(256), (size_t)(smem), st, low, (const long long*)labels, mask, counts, C, g, S, chunks);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -977,8 +997,7 @@ static void launch_upsample_ce(const float* low, const void* labels, int LH, int
   const unsigned grid = (unsigned)((nreg + kWarps - 1) / kWarps);
   // the scale PyTorch's nearest kernel uses: (float)input_size / output_size
   const float sy = (float)LH / (float)S, sx = (float)LW / (float)S;
-  upsample_ce_kernel<CMAX, LabelT><<<grid, kWarps * 32, 0, st>>>(low, (const LabelT*)labels, LH, LW, sy, sx, loss_sum,
-                                                                  dlow, B, C, g, S);
+  launch_k(upsample_ce_kernel<CMAX, LabelT>, dim3(grid), dim3(kWarps * 32), (size_t)(0), st, low, (const LabelT*)labels, LH, LW, sy, sx, loss_sum, dlow, B, C, g, S);
 }
 
 extern "C" int vs_upsample_ce(const float* low, const void* labels, int32_t label_dtype, int32_t LH, int32_t LW,
@@ -1010,8 +1029,7 @@ extern "C" int vs_paed_binary_stats(const float* low, const float* mask, const f
   if (int rc = check_grid("vs_paed_binary_stats", B, 1, g, S)) return rc;
   VS_CHECK_ARG(g <= kMaxG, "vs_paed_binary_stats: g must be <= %d", kMaxG);
   const long long nreg = (long long)B * (g + 1) * (g + 1);
-  paed_binary_stats_kernel<<<(unsigned)nreg, 256, 0, (cudaStream_t)stream>>>(low, mask, sdf_ext, sdf_int, stats,
-                                                                            (unsigned long long*)keys, B, g, S);
+  launch_k(paed_binary_stats_kernel, dim3((unsigned)nreg), dim3(256), (size_t)(0), (cudaStream_t)stream, low, mask, sdf_ext, sdf_int, stats, (unsigned long long*)keys, B, g, S);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -1023,8 +1041,7 @@ extern "C" int vs_paed_binary_bwd(const float* low, const float* mask, const flo
   if (int rc = check_grid("vs_paed_binary_bwd", B, 1, g, S)) return rc;
   VS_CHECK_ARG(g <= kMaxG, "vs_paed_binary_bwd: g must be <= %d", kMaxG);
   const long long nreg = (long long)B * (g + 1) * (g + 1);
-  paed_binary_bwd_kernel<<<(unsigned)nreg, 256, 0, (cudaStream_t)stream>>>(low, mask, sdf_ext, sdf_int, coef,
-                                                                          (const unsigned long long*)keys, dlow, B, g, S);
+  launch_k(paed_binary_bwd_kernel, dim3((unsigned)nreg), dim3(256), (size_t)(0), (cudaStream_t)stream, low, mask, sdf_ext, sdf_int, coef, (const unsigned long long*)keys, dlow, B, g, S);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -1042,15 +1059,15 @@ static int paed_multiclass_impl(const float* low, const long long* labels, float
   }
   const long long planes = (long long)B * C;
   // t1 = onehot - p ; t2 = blur(t1) = t
-  pm_pixel_kernel<CMAX><<<B * chunks, 256, smem, st>>>(low, labels, nullptr, nullptr, t1, nullptr, 0, C, g, S, chunks);
+  launch_k(pm_pixel_kernel<CMAX>, dim3(B * chunks), dim3(256), (size_t)(smem), st, low, labels, nullptr, nullptr, t1, nullptr, 0, C, g, S, chunks);
   if (int rc = launch_blur2d(t1, t2, planes, S, st)) return rc;
   // loss and u -> t1 (reads t only at the label channel)
-  pm_pixel_kernel<CMAX><<<B * chunks, 256, smem, st>>>(low, labels, t2, nullptr, t1, loss_sum, 1, C, g, S, chunks);
+  launch_k(pm_pixel_kernel<CMAX>, dim3(B * chunks), dim3(256), (size_t)(smem), st, low, labels, t2, nullptr, t1, loss_sum, 1, C, g, S, chunks);
   VS_CHECK_LAUNCH();
   if (dlow != nullptr) {
     // t3 = blur(u) ; t1 = d(loss)/d(upsampled logits) ; dlow = upsample^T(t1)
     if (int rc = launch_blur2d(t1, t3, planes, S, st)) return rc;
-    pm_pixel_kernel<CMAX><<<B * chunks, 256, smem, st>>>(low, labels, t2, t3, t1, nullptr, 2, C, g, S, chunks);
+    launch_k(pm_pixel_kernel<CMAX>, dim3(B * chunks), dim3(256), (size_t)(smem), st, low, labels, t2, t3, t1, nullptr, 2, C, g, S, chunks);
     VS_CHECK_LAUNCH();
     return vs_upsample_bilinear_bwd(t1, dlow, B, C, g, S, (void*)st);
   }
@@ -1088,12 +1105,12 @@ extern "C" int vs_paed_multiclass_dense(const float* msk, const float* prob, flo
   if (bg > (long long)nsm * 32) bg = (long long)nsm * 32;
   const unsigned grid = (unsigned)bg;
   // t1 = m - p ; t2 = blur(t1) = t ; t1 = u ; t3 = blur(u) ; dprob
-  pmd_elem_kernel<<<grid, 256, 0, st>>>(msk, prob, nullptr, nullptr, t1, nullptr, n, 0, class_penalty);
+  launch_k(pmd_elem_kernel, dim3(grid), dim3(256), (size_t)(0), st, msk, prob, nullptr, nullptr, t1, nullptr, n, 0, class_penalty);
   if (int rc = launch_blur2d(t1, t2, planes, S, st)) return rc;
-  pmd_elem_kernel<<<grid, 256, 0, st>>>(msk, prob, t2, nullptr, t1, loss_sum, n, 1, class_penalty);
+  launch_k(pmd_elem_kernel, dim3(grid), dim3(256), (size_t)(0), st, msk, prob, t2, nullptr, t1, loss_sum, n, 1, class_penalty);
   if (dprob != nullptr) {
     if (int rc = launch_blur2d(t1, t3, planes, S, st)) return rc;
-    pmd_elem_kernel<<<grid, 256, 0, st>>>(msk, prob, t2, t3, dprob, nullptr, n, 2, class_penalty);
+    launch_k(pmd_elem_kernel, dim3(grid), dim3(256), (size_t)(0), st, msk, prob, t2, t3, dprob, nullptr, n, 2, class_penalty);
   }
   VS_CHECK_LAUNCH();
   return 0;

@@ -11,44 +11,70 @@ namespace vs {
 // column sums of a bf16 matrix: out[n] (+)= sum_m x[m, n]
 // block = 256 threads = 32 column groups (8 bf16 = 16 B each) x 8 row lanes; grid.y splits the rows
 // ------------------------------------------------------------------------------------------------
+// FUSED_CAST: the first `nf` columns are still fp32 (xf: the dQ accumulator of the attention backward); they are rounded
+// to bf16, written into x (so the QKV weight / data gradient GEMMs can read one bf16 matrix) and summed from the rounded
+// values — replaces the separate cast pass over dQ (r01: cast_rows_kernel, 12 launches, 1.3 % of the step).
+template <bool FUSED_CAST>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int M, int N, float* __restrict__ out) {
+colsum_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int M, int N, float* __restrict__ out,
+              const float* __restrict__ xf, long long ldf, int nf) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][256 + 8];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cg) * 8;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  auto add8 = [&](const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(w[i]);
+      acc[2 * i] += f.x;
+      acc[2 * i + 1] += f.y;
+    }
+  };
   if (col < N) {
     const int rows_per = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-    // four independent 16-byte loads in flight per thread: the inputs are L2-resident (just written by the producing
-    // GEMM), so the loop is bound by load latency, not bandwidth
-    int r = r0 + rl;
-    for (; r + 24 < r1; r += 32) {
-      uint4 v[4];
+    if (FUSED_CAST && col < nf) {
+      int r = r0 + rl;
+      for (; r + 8 < r1; r += 16) {   // two rows (4 x 16-byte loads) in flight per thread
+        float4 a[2][2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (long long)(r + 8 * u) * ldx + col);
+        for (int u = 0; u < 2; ++u) {
+          const float* src = xf + (long long)(r + 8 * u) * ldf + col;
+          a[u][0] = *reinterpret_cast<const float4*>(src);
+          a[u][1] = *reinterpret_cast<const float4*>(src + 4);
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_bf16(w[i]);
-          acc[2 * i] += f.x;
-          acc[2 * i + 1] += f.y;
+        for (int u = 0; u < 2; ++u) {
+          const uint4 v = make_uint4(pack_bf16(a[u][0].x, a[u][0].y), pack_bf16(a[u][0].z, a[u][0].w),
+                                     pack_bf16(a[u][1].x, a[u][1].y), pack_bf16(a[u][1].z, a[u][1].w));
+          *reinterpret_cast<uint4*>(x + (long long)(r + 8 * u) * ldx + col) = v;
+          add8(v);
         }
       }
-    }
-    for (; r < r1; r += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(x + (long long)r * ldx + col);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16(w[i]);
-        acc[2 * i] += f.x;
-        acc[2 * i + 1] += f.y;
+      for (; r < r1; r += 8) {
+        const float* src = xf + (long long)r * ldf + col;
+        const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+        const uint4 v = make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
+        *reinterpret_cast<uint4*>(x + (long long)r * ldx + col) = v;
+        add8(v);
       }
+    } else {
+      // four independent 16-byte loads in flight per thread: the inputs are L2-resident (just written by the producing
+      // GEMM), so the loop is bound by load latency, not bandwidth
+      int r = r0 + rl;
+      for (; r + 24 < r1; r += 32) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + (long long)(r + 8 * u) * ldx + col);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) add8(v[u]);
+      }
+      for (; r < r1; r += 8) add8(*reinterpret_cast<const uint4*>(x + (long long)r * ldx + col));
     }
   }
 #pragma unroll
@@ -66,6 +92,8 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int M, int N, 
 // patchify: NCHW fp32 image -> bf16 [B*T, 3*P*P] with K = (c, ph, pw); 4 pixels per thread
 // ------------------------------------------------------------------------------------------------
 __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int P) {
+  pdl_wait();
+  pdl_trigger();
   const int gp = S / P;
   const int K = 3 * P * P;
   const long long total = (long long)B * gp * gp * (K / 4);
@@ -86,6 +114,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                                 int B, int T1, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   const int b = idx / D, d = idx - b * D;
@@ -95,6 +125,8 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 // dpos[t, d] += sum_b dx[b, t, d]; dcls[d] += sum_b dx[b, 0, d]
 __global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
                                  float* __restrict__ dbias, int B, int T1, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over T1 * D/4
   const int D4 = D / 4;
   if (idx >= T1 * D4) return;
@@ -124,6 +156,8 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void head_im2col_kernel(const __nv_bfloat16* __restrict__ tok, __nv_bfloat16* __restrict__ col, int B, int g,
                                    int D) {
+  pdl_wait();
+  pdl_trigger();
   const int D8 = D / 8;
   const long long total = (long long)B * g * g * 9 * D8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -145,6 +179,8 @@ __global__ void head_im2col_kernel(const __nv_bfloat16* __restrict__ tok, __nv_b
 
 // adjoint of im2col: dtok[b, 1 + y*g + x, c] = sum_{ky,kx} dcol[(b, y-ky+1, x-kx+1), (ky,kx,c)]; CLS row = 0
 __global__ void head_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dtok, int B, int g, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int D8 = D / 8;
   const int T1 = g * g + 1;
   const long long total = (long long)B * T1 * D8;
@@ -186,6 +222,8 @@ __global__ void head_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, float
 __global__ void __launch_bounds__(256)
 conv1x1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ logits, int B, int T, int F, int C) {
+  pdl_wait();
+  pdl_trigger();
   // weights as [C][F/256][8][32]: lane l holds features 8l .. 8l+7 of a 256-chunk (one 16-byte load), and reads
   // weight (i, l) at word i*32 + l — conflict-free (the plain [C][F] layout put 8 lanes on every bank: 60 us, ncu r01)
   extern __shared__ float s_w[];
@@ -240,6 +278,8 @@ __global__ void __launch_bounds__(256)
 conv1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ feat, const float* __restrict__ w,
                    __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db, int B, int T,
                    int F, int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_dl[64][kMaxClasses];
   __shared__ __align__(16) __nv_bfloat16 s_x[64][256];   // feature rows of the current pixel group (F <= 256)
   const int f = threadIdx.x;
@@ -319,6 +359,8 @@ conv1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
 // casts / packing
 // ------------------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
@@ -332,6 +374,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 
 __global__ void cast_rows_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
                                  long long ldd, int M, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int D4 = D / 4;
   const long long total = (long long)M * D4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -344,6 +388,8 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, long long lds, _
 
 // OIHW fp32 [O, I, 3, 3] -> bf16 [O, (ky, kx, I)]
 __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)O * I * 9;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -355,6 +401,8 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 // grad fp32 [O, (ky,kx,I)] -> dw OIHW +=
 __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ g, float* __restrict__ dw, int O, int I) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)O * I * 9;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -369,6 +417,8 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ g, float* _
 // Used for the embedding dropout (TF:126) forward and — same mask — on the gradient in backward.
 __global__ void dropout_rows_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ x16, long long n4,
                                     const DropCfg drop) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t sd = drop_seed(drop);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<float4*>(x)[i];
@@ -388,6 +438,8 @@ __global__ void dropout_rows_kernel(float* __restrict__ x, __nv_bfloat16* __rest
 // states), scheme 1 = attention probabilities viewed as [n / row_len, row_len].  Test / debugging aid.
 __global__ void dropout_mask_kernel(uint8_t* __restrict__ out, long long n, int scheme, int row_len,
                                     const DropCfg drop) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t sd = drop_seed(drop);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     bool keep;
@@ -421,20 +473,37 @@ static inline int grid_for(long long total, int block, int nsm) {
 
 using namespace vs;
 
-extern "C" int vs_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate,
-                              void* stream) {
-  VS_CHECK_ARG(x && out && M > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0, "vs_colsum_bf16: bad arguments");
+static int colsum_launch(void* x, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate, const float* xf,
+                         int64_t ldf, int32_t nf, cudaStream_t st) {
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_colsum_bf16: no CUDA device");
-  cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) VS_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
   const int gx = (N + 255) / 256;
   int gy = (nsm * 4 + gx - 1) / gx;
   if (gy > (M + 63) / 64) gy = (M + 63) / 64;
   if (gy < 1) gy = 1;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, M, N, out);
+  if (xf != nullptr)
+    launch_k(colsum_kernel<true>, dim3(gx, gy), dim3(256), (size_t)0, st, (__nv_bfloat16*)x, (long long)ldx, M, N, out, xf,
+             (long long)ldf, nf);
+  else
+    launch_k(colsum_kernel<false>, dim3(gx, gy), dim3(256), (size_t)0, st, (__nv_bfloat16*)x, (long long)ldx, M, N, out,
+             (const float*)nullptr, 0LL, 0);
   VS_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int vs_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate,
+                              void* stream) {
+  VS_CHECK_ARG(x && out && M > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0, "vs_colsum_bf16: bad arguments");
+  return colsum_launch(const_cast<void*>(x), ldx, M, N, out, accumulate, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int vs_colsum_cast_bf16(void* x, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate,
+                                   const float* x_f32, int64_t ldf, int32_t nf, void* stream) {
+  VS_CHECK_ARG(x && out && x_f32 && M > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0, "vs_colsum_cast_bf16: bad arguments");
+  VS_CHECK_ARG(nf > 0 && nf <= N && nf % 8 == 0 && ldf % 4 == 0 && (uintptr_t)x_f32 % 16 == 0,
+               "vs_colsum_cast_bf16: the fp32 column block must be a multiple of 8 columns, 16-byte aligned");
+  return colsum_launch(x, ldx, M, N, out, accumulate, x_f32, ldf, nf, (cudaStream_t)stream);
 }
 
 extern "C" int vs_patchify(const float* img, void* out, int32_t B, int32_t S, int32_t P, void* stream) {
@@ -442,7 +511,7 @@ extern "C" int vs_patchify(const float* img, void* out, int32_t B, int32_t S, in
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_patchify: no CUDA device");
   const long long total = (long long)B * (S / P) * (S / P) * (3 * P * P / 4);
-  patchify_kernel<<<grid_for(total, 256, nsm), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)out, B, S, P);
+  launch_k(patchify_kernel, dim3(grid_for(total, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, img, (__nv_bfloat16*)out, B, S, P);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -450,7 +519,7 @@ extern "C" int vs_patchify(const float* img, void* out, int32_t B, int32_t S, in
 extern "C" int vs_cls_rows(const float* cls, const float* pos, float* x, int32_t B, int32_t T1, int32_t D, void* stream) {
   VS_CHECK_ARG(cls && pos && x && B > 0 && T1 > 0 && D > 0, "vs_cls_rows: bad arguments");
   VS_CHECK_ARG(sm_count() > 0, "vs_cls_rows: no CUDA device");
-  cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, pos, x, B, T1, D);
+  launch_k(cls_rows_kernel, dim3((B * D + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, cls, pos, x, B, T1, D);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -460,7 +529,7 @@ extern "C" int vs_embed_bwd(const float* dx, float* dcls, float* dpos, float* db
   VS_CHECK_ARG(dx && dcls && dpos && dbias && B > 0 && T1 > 0 && D % 4 == 0, "vs_embed_bwd: bad arguments");
   VS_CHECK_ARG(sm_count() > 0, "vs_embed_bwd: no CUDA device");
   const int total = T1 * (D / 4);
-  embed_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dx, dcls, dpos, dbias, B, T1, D);
+  launch_k(embed_bwd_kernel, dim3((total + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, dx, dcls, dpos, dbias, B, T1, D);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -470,8 +539,7 @@ extern "C" int vs_head_im2col(const void* tokens, void* col, int32_t B, int32_t 
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_head_im2col: no CUDA device");
   const long long total = (long long)B * g * g * 9 * (D / 8);
-  head_im2col_kernel<<<grid_for(total, 256, nsm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)tokens,
-                                                                                  (__nv_bfloat16*)col, B, g, D);
+  launch_k(head_im2col_kernel, dim3(grid_for(total, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)tokens, (__nv_bfloat16*)col, B, g, D);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -481,8 +549,7 @@ extern "C" int vs_head_col2im(const void* dcol, float* dtokens, int32_t B, int32
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_head_col2im: no CUDA device");
   const long long total = (long long)B * (g * g + 1) * (D / 8);
-  head_col2im_kernel<<<grid_for(total, 256, nsm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, dtokens, B,
-                                                                                  g, D);
+  launch_k(head_col2im_kernel, dim3(grid_for(total, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)dcol, dtokens, B, g, D);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -503,7 +570,7 @@ extern "C" int vs_conv1x1_fwd(const void* feat, const float* w, const float* b, 
   const long long npix = (long long)B * g * g;
   int grid = (int)((npix + 7) / 8);
   if (grid > nsm * 8) grid = nsm * 8;
-  conv1x1_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)feat, w, b, logits, B, g * g, F, C);
+  launch_k(conv1x1_fwd_kernel, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, (const __nv_bfloat16*)feat, w, b, logits, B, g * g, F, C);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -519,8 +586,7 @@ extern "C" int vs_conv1x1_bwd(const float* dlogits, const void* feat, const floa
   VS_CHECK_ARG((uintptr_t)dw % 16 == 0, "vs_conv1x1_bwd: dw must be 16-byte aligned");
   int grid = nsm;
   if (grid > (npix + 63) / 64) grid = (int)((npix + 63) / 64);
-  conv1x1_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dlogits, (const __nv_bfloat16*)feat, w,
-                                                             (__nv_bfloat16*)dfeat, dw, db, B, g * g, F, C);
+  launch_k(conv1x1_bwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, dlogits, (const __nv_bfloat16*)feat, w, (__nv_bfloat16*)dfeat, dw, db, B, g * g, F, C);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -530,7 +596,7 @@ extern "C" int vs_cast_f32_bf16(const float* src, void* dst, int64_t n, void* st
   VS_CHECK_ARG(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "vs_cast_f32_bf16: misaligned");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_cast_f32_bf16: no CUDA device");
-  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256, nsm), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  launch_k(cast_f32_bf16_kernel, dim3(grid_for(n / 4 + 1, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -540,8 +606,7 @@ extern "C" int vs_cast_bf16_rows(const float* src, int64_t lds, void* dst, int64
   VS_CHECK_ARG(src && dst && M > 0 && D > 0 && D % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vs_cast_bf16_rows: bad arguments");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_cast_bf16_rows: no CUDA device");
-  cast_rows_kernel<<<grid_for((long long)M * D / 4, 256, nsm), 256, 0, (cudaStream_t)stream>>>(
-      src, lds, (__nv_bfloat16*)dst, ldd, M, D);
+  launch_k(cast_rows_kernel, dim3(grid_for((long long)M * D / 4, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, src, lds, (__nv_bfloat16*)dst, ldd, M, D);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -550,8 +615,7 @@ extern "C" int vs_pack_conv3x3(const float* w, void* out, int32_t O, int32_t I, 
   VS_CHECK_ARG(w && out && O > 0 && I > 0, "vs_pack_conv3x3: bad arguments");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_pack_conv3x3: no CUDA device");
-  pack_conv3x3_kernel<<<grid_for((long long)O * I * 9, 256, nsm), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out,
-                                                                                                 O, I);
+  launch_k(pack_conv3x3_kernel, dim3(grid_for((long long)O * I * 9, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, w, (__nv_bfloat16*)out, O, I);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -560,7 +624,7 @@ extern "C" int vs_unpack_conv3x3_grad(const float* g, float* dw, int32_t O, int3
   VS_CHECK_ARG(g && dw && O > 0 && I > 0, "vs_unpack_conv3x3_grad: bad arguments");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_unpack_conv3x3_grad: no CUDA device");
-  unpack_conv3x3_grad_kernel<<<grid_for((long long)O * I * 9, 256, nsm), 256, 0, (cudaStream_t)stream>>>(g, dw, O, I);
+  launch_k(unpack_conv3x3_grad_kernel, dim3(grid_for((long long)O * I * 9, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, g, dw, O, I);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -584,7 +648,7 @@ extern "C" int vs_dropout_rows(float* x, void* x_bf16, int64_t n, float dropout_
   VS_CHECK_ARG(nsm > 0, "vs_dropout_rows: no CUDA device");
   DropCfg dc;
   if (int rc = make_drop_cfg(&dc, dropout_p, dropout_seed, dropout_site, "vs_dropout_rows")) return rc;
-  dropout_rows_kernel<<<grid_for(n / 4, 256, nsm), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)x_bf16, n / 4, dc);
+  launch_k(dropout_rows_kernel, dim3(grid_for(n / 4, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (__nv_bfloat16*)x_bf16, n / 4, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -597,7 +661,7 @@ extern "C" int vs_dropout_mask(uint8_t* out, int64_t n, int32_t scheme, int32_t 
   VS_CHECK_ARG(nsm > 0, "vs_dropout_mask: no CUDA device");
   DropCfg dc;
   if (int rc = make_drop_cfg(&dc, dropout_p, dropout_seed, dropout_site, "vs_dropout_mask")) return rc;
-  dropout_mask_kernel<<<grid_for(n, 256, nsm), 256, 0, (cudaStream_t)stream>>>(out, n, scheme, row_len, dc);
+  launch_k(dropout_mask_kernel, dim3(grid_for(n, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, out, n, scheme, row_len, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -614,6 +678,8 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
             __nv_bfloat16* __restrict__ shadow, long long n4, const float* __restrict__ lr_ptr,
             const int* __restrict__ step_ptr, float beta1, float beta2, float eps, float wd, int decoupled,
             float grad_scale, int zero_grad, long long skip_begin4, long long skip_end4) {
+  pdl_wait();
+  pdl_trigger();
   const float lr = lr_ptr[0];
   const float t = (float)step_ptr[0];
   const float bc1 = 1.0f - exp2f(t * log2f(beta1));
@@ -658,9 +724,7 @@ extern "C" int vs_adam_step(float* param, float* grad, float* exp_avg, float* ex
                "vs_adam_step: n and the skip range must be multiples of 4");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_adam_step: no CUDA device");
-  adam_kernel<<<nsm * 8, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16,
-                                                        n / 4, lr_dev, step_dev, beta1, beta2, eps, weight_decay,
-                                                        decoupled, grad_scale, zero_grad, skip_begin / 4, skip_end / 4);
+  launch_k(adam_kernel, dim3(nsm * 8), dim3(256), (size_t)(0), (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n / 4, lr_dev, step_dev, beta1, beta2, eps, weight_decay, decoupled, grad_scale, zero_grad, skip_begin / 4, skip_end / 4);
   VS_CHECK_LAUNCH();
   return 0;
 }

@@ -1,6 +1,7 @@
 // Host-side runtime pieces of libvitseg: error string, device query, TMA descriptor encoding.
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VS_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 int sm_count() {

@@ -19,6 +19,8 @@ constexpr int kSdfNone = 0xFFFF;
 // one warp per (variant, image, row): lanes sweep the row in chunks of 32 with ballots
 __global__ void __launch_bounds__(256)
 sdf_rows_kernel(const float* __restrict__ mask, uint16_t* __restrict__ d1, int* __restrict__ has_zero, int B, int S) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row_id = (long long)blockIdx.x * 8 + warp;
   if (row_id >= 2LL * B * S) return;
@@ -57,6 +59,8 @@ sdf_rows_kernel(const float* __restrict__ mask, uint16_t* __restrict__ d1, int* 
 __global__ void __launch_bounds__(256)
 sdf_cols_kernel(const uint16_t* __restrict__ d1, const int* __restrict__ has_zero, float* __restrict__ out_ext,
                 float* __restrict__ out_int, unsigned* __restrict__ vmax, int B, int S) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint16_t s_d1[];   // [S][32]
   const int x0 = blockIdx.x * 32, b = blockIdx.y, v = blockIdx.z;
   const uint16_t* src = d1 + ((long long)v * B + b) * S * S;
@@ -94,6 +98,8 @@ sdf_cols_kernel(const uint16_t* __restrict__ d1, const int* __restrict__ has_zer
 
 __global__ void sdf_normalise_kernel(float* __restrict__ out_ext, float* __restrict__ out_int,
                                      const unsigned* __restrict__ vmax, int B, int S) {
+  pdl_wait();
+  pdl_trigger();
   const long long n = (long long)B * S * S;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (long long)gridDim.x * blockDim.x) {
     const int v = int(i / n);
@@ -127,17 +133,17 @@ extern "C" int vs_sdf_targets(const float* mask, float* sdf_ext, float* sdf_int,
   uint16_t* d1 = reinterpret_cast<uint16_t*>(flags + 4 * B);
   VS_CHECK_CUDA(cudaMemsetAsync(flags, 0, (size_t)4 * B * sizeof(int), st));
   const long long rows = 2LL * B * S;
-  sdf_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(mask, d1, flags, B, S);
+  launch_k(sdf_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), st, mask, d1, flags, B, S);
   const size_t smem = (size_t)S * 32 * sizeof(uint16_t);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(sdf_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  sdf_cols_kernel<<<dim3((S + 31) / 32, B, 2), 256, smem, st>>>(d1, flags, sdf_ext, sdf_int, vmax, B, S);
+  launch_k(sdf_cols_kernel, dim3(dim3((S + 31) / 32, B, 2)), dim3(256), (size_t)(smem), st, d1, flags, sdf_ext, sdf_int, vmax, B, S);
   long long nb = (2LL * B * S * S + 255) / 256;
   if (nb > (long long)nsm * 16) nb = (long long)nsm * 16;
-  sdf_normalise_kernel<<<(unsigned)nb, 256, 0, st>>>(sdf_ext, sdf_int, vmax, B, S);
+  launch_k(sdf_normalise_kernel, dim3((unsigned)nb), dim3(256), (size_t)(0), st, sdf_ext, sdf_int, vmax, B, S);
   VS_CHECK_LAUNCH();
   return 0;
 }

@@ -449,11 +449,11 @@ class Engine:
             # attention core
             K.attention_bwd(ws["qkv"][i], ws["ctx"][i], ws["dctx"], ws["lse"][i], ws["dqkv"], ws["dq_acc"], ws["delta"],
                             B, T1, H, scale, dropout=self._site(p_att, 1000 + i))
-            K.cast_bf16_rows(ws["dq_acc"], ws["dqkv"][:, :D])
-            # fused QKV projection
+            # fused QKV projection; its bias gradient (column sums of dQKV) and the bf16 copy of the fp32 dQ
+            # accumulator come out of one pass
             gw, gb = self.fused_qkv(i, arena="grads")
             wqkv, _ = self.fused_qkv(i)
-            K.colsum(ws["dqkv"], gb, accumulate=True)
+            K.colsum_cast(ws["dqkv"], ws["dq_acc"], gb, accumulate=True)
             K.gemm(ws["dqkv"], ws["ln1"][i], gw, a_mn=True, b_mn=True, accumulate=True)
             K.gemm(ws["dqkv"], wqkv, ws["d_ln"], b_mn=True)
             # LN1 + skip
@@ -464,7 +464,7 @@ class Engine:
                             dropout=self._site(p_hid, 2 * i) if i > 0 else None,
                             dbias=self.g32(f"backbone.encoder.layer.{i - 1}.output.dense.bias") if i > 0 else None)
             dx, dx_other = dx_other, dx
-            n += 17
+            n += 16
             if hook:
                 hook(f"layer{i}")
         # --- embeddings

@@ -5,6 +5,7 @@ tensors and raises otherwise — nothing here falls back to PyTorch math."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -57,6 +58,56 @@ def _rowmajor(t: torch.Tensor, what: str) -> int:
     return t.stride(0)
 
 
+# --- tile-configuration autotuning ---------------------------------------------------------------------------------
+# The library's cost model (gemm.cu: choose_tiles) is a fit over a handful of shapes; which of the five tile
+# configurations wins depends on the epilogue (bf16 TMA-store vs fp32 transposed vs atomics) as much as on the shape.
+# The first eager call of every (shape, operand majors, epilogue) combination therefore times the five candidates on
+# the real operands (CUDA events, 2 warm-up + 4 timed launches each) and caches the winner; calls made while a CUDA
+# graph is being captured use the cache (or the cost model if the shape was never seen eagerly).
+# VS_GEMM_AUTOTUNE=0 turns it off.
+_AUTOTUNE = os.environ.get("VS_GEMM_AUTOTUNE", "1") != "0"
+_TUNED = {}
+
+
+def _autotune(d, out, accumulate):
+    lib = _lib.load()
+    st = stream()
+    saved_out = d.out
+    scratch = None
+    if accumulate:   # trial launches must not add into the caller's gradient buffer
+        scratch = torch.empty_like(out)
+        d.out, d.ldo = ptr(scratch), scratch.stride(0)
+    best, best_ms = 0, float("inf")
+    try:
+        for cfg in (1, 2, 3, 4, 5):
+            d.tile_cfg = cfg
+            ok = True
+            for _ in range(2):
+                ok = ok and lib.vs_gemm_bf16(C.byref(d), st) == 0
+            if not ok:
+                continue
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(4):
+                lib.vs_gemm_bf16(C.byref(d), st)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if ms < best_ms:
+                best, best_ms = cfg, ms
+    finally:
+        d.out = saved_out
+        if accumulate:
+            d.ldo = out.stride(0)
+        d.tile_cfg = 0
+    return best
+
+
+def tuned_configs():
+    """{(M, N, K, a_mn, b_mn, ...): tile_cfg} chosen so far (bench.py / tools report it)."""
+    return dict(_TUNED)
+
+
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=None, aux=None, aux_mode=AUX_NONE,
          residual=None, row_tokens=0, accumulate=False, split_k=0, tile_cfg=0, M=None, N=None, K=None,
          dropout=None):
@@ -99,6 +150,13 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=Non
     d.tile_cfg = tile_cfg
     if dropout is not None and dropout[0] > 0.0:   # (p, seed tensor (uint32/int32 device), site)
         d.dropout_p, d.dropout_seed, d.dropout_site = dropout[0], ptr(dropout[1]), dropout[2]
+    if tile_cfg == 0 and _AUTOTUNE:
+        key = (M, N, K, bool(a_mn), bool(b_mn), d.out_dtype, bool(accumulate), bias is not None, act, out2 is not None,
+               aux_mode, residual is not None, row_tokens > 0, d.dropout_p > 0.0, split_k)
+        cfg = _TUNED.get(key)
+        if cfg is None and not torch.cuda.is_current_stream_capturing():
+            cfg = _TUNED[key] = _autotune(d, out, accumulate)
+        d.tile_cfg = cfg or 0
     if _GEMM_TIMING:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -117,6 +175,18 @@ def colsum(x, out, accumulate=True):
     _count(1)
     check(_lib.load().vs_colsum_bf16(ptr(x), _rowmajor(x, "x"), x.shape[0], x.shape[1], ptr(out), int(accumulate),
                                     stream()), "vs_colsum_bf16")
+    return out
+
+
+def colsum_cast(x, x_f32, out, accumulate=True):
+    """column sums of bf16 x [M,N] whose first x_f32.shape[1] columns are taken from fp32 x_f32 (rounded and stored
+    into x on the way): dQKV bias gradient + dQ cast in one pass."""
+    require_cuda(x, "colsum_cast")
+    assert x.dtype == BF16 and x_f32.dtype == F32 and out.dtype == F32 and x_f32.shape[0] == x.shape[0]
+    _count(1)
+    check(_lib.load().vs_colsum_cast_bf16(ptr(x), _rowmajor(x, "x"), x.shape[0], x.shape[1], ptr(out), int(accumulate),
+                                         ptr(x_f32), _rowmajor(x_f32, "x_f32"), x_f32.shape[1], stream()),
+          "vs_colsum_cast_bf16")
     return out
 
 
@@ -271,6 +341,34 @@ def colorize_mask(mask, palette):
     check(_lib.load().vs_colorize_mask(ptr(mask), ptr(palette), ptr(rgb), mask.numel(), palette.shape[0], stream()),
           "vs_colorize_mask")
     return rgb
+
+
+def resample_h(src, bounds, coef, ksize, wout, dst):
+    """uint8 [C,H,W] (last dim contiguous) -> uint8 [C,H,wout]: Pillow's horizontal resampling pass."""
+    require_cuda(src, "resample_h")
+    assert src.dtype == torch.uint8 and src.dim() == 3 and src.stride(2) == 1
+    Cn, H, W = src.shape
+    _count(1)
+    check(_lib.load().vs_resample_h_u8(ptr(src), src.stride(1), src.stride(0), Cn, H, W, ptr(bounds), ptr(coef), ksize,
+                                       wout, ptr(dst), stream()), "vs_resample_h_u8")
+    return dst
+
+
+def resample_v(src, bounds, coef, ksize, hout, dst_f32=None, scale=1.0 / 255.0, dst_u8=None):
+    """uint8 [C,H,W] contiguous -> [C,hout,W]: Pillow's vertical pass; fp32 (value * scale) and/or uint8 output."""
+    require_cuda(src, "resample_v")
+    assert src.dtype == torch.uint8 and src.is_contiguous()
+    Cn, H, W = src.shape
+    _count(1)
+    check(_lib.load().vs_resample_v_u8(ptr(src), Cn, H, W, ptr(bounds), ptr(coef), ksize, hout, ptr(dst_f32), scale,
+                                       ptr(dst_u8), stream()), "vs_resample_v_u8")
+
+
+def u8_to_f32(src, dst, scale=1.0 / 255.0):
+    require_cuda(src, "u8_to_f32")
+    assert src.dtype == torch.uint8 and src.is_contiguous() and dst.dtype == F32 and dst.is_contiguous()
+    _count(1)
+    check(_lib.load().vs_u8_to_f32(ptr(src), ptr(dst), src.numel(), scale, stream()), "vs_u8_to_f32")
 
 
 def sdf_targets(mask):
