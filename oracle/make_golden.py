@@ -311,23 +311,34 @@ def headline():
 
 
 def curve(steps: int = 200):
-    """200 optimisation steps of the UNMODIFIED reference CE module with its own optimizer
-    (LightningViTModel.configure_optimizers: Adam lr 1e-5, CE:296-297) on fixed batches, dropout off: the loss curve the
-    CUDA path has to follow within 1 % per step (north_star)."""
+    """200 optimisation steps of the UNMODIFIED reference CE module (model/CE/classes.py:276-297) on a fixed batch,
+    dropout off: the loss curves the CUDA path has to follow (north_star: within 1 %).
+      'adam_lr1e-5': the reference's own optimizer, ref.configure_optimizers() = Adam(lr=1e-5);
+      'adam_lr3e-6': the same optimizer object with lr = 3e-6 (a regime without Adam's sign-descent loss spikes, where a
+                     per-step 1 % bound is meaningful: see tests/test_headline_gpu.py).
+    Weights: fp32 random init NOT snapped to bf16 (north_star: 'random-init weights').  Snapping the initial weights to
+    the bf16 grid, as the single-step parity fixtures do, makes any bf16-operand implementation lag the fp32 run by
+    several steps at these learning rates (every weight must first travel half a bf16 ulp before its rounded copy
+    moves), which is an artefact of the fixture, not of the implementation."""
     import time
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 8)
     ce = load_reference("CE")
     cfgb = O.OracleConfig(num_classes=17, patch_size=16, hidden_size=768, num_hidden_layers=12, num_attention_heads=12)
-    out = {"cfg": cfgb.__dict__, "weights_seed": 31, "head_gain": 1.0, "steps": steps, "optimizer": "Adam(lr=1e-5)"}
-    for task in ("regions", "brightness"):
+    task = dict(block=32, noise=0.5, contrast=0.8)
+    out = {"cfg": cfgb.__dict__, "weights_seed": 31, "head_gain": 1.0, "bf16_representable": False, "steps": steps,
+           "task": task, "curves": {}}
+    for name, lr in (("adam_lr1e-5", None), ("adam_lr3e-6", 3e-6)):
         t0 = time.time()
-        sd = O.seeded_state_dict(cfgb, seed=31, head_gain=1.0)
-        x, y = O.curve_task(task)
+        sd = O.seeded_state_dict(cfgb, seed=31, head_gain=1.0, bf16_representable=False)
+        x, y = O.curve_task("regions", **task)
         ref = ce.LightningViTModel(17, 16, 768, 12, 12)
         ref.load_state_dict(O.to_module_state_dict(sd, "model."), strict=True)
         ref.eval()   # dropout off; training_step / backward / optimizer are unaffected by eval()
         opt = ref.configure_optimizers()
+        if lr is not None:
+            for g in opt.param_groups:
+                g["lr"] = lr
         losses = []
         for i in range(steps):
             loss = ref.training_step((x, y), i)     # labels already 224x224: _resize_target is the identity
@@ -336,8 +347,8 @@ def curve(steps: int = 200):
             opt.step()
             losses.append(loss.item())
             if i % 20 == 0:
-                print(task, i, losses[-1], f"{time.time() - t0:.0f}s", flush=True)
-        out[task] = torch.tensor(losses, dtype=torch.float64)
+                print(name, i, losses[-1], f"{time.time() - t0:.0f}s", flush=True)
+        out["curves"][name] = {"lr": opt.param_groups[0]["lr"], "loss": torch.tensor(losses, dtype=torch.float64)}
         del ref, opt
     torch.save(out, os.path.join(GOLD, "vitb16_curve.pt"))
     print("vitb16_curve golden written")

@@ -156,7 +156,26 @@ def probe_gemm():
     run("gemm patch", patch_case)
 
 
+def probe_colsum():
+    def f():
+        for M, N, nf in ((12608, 2304, 768), (197, 384, 128), (1000, 3072, 1024)):
+            x = bf(torch.randn(M, N, device=dev))
+            xf = torch.randn(M, nf, device=dev)
+            want_x = x.clone()
+            want_x[:, :nf] = bf(xf)
+            out = torch.randn(N, device=dev)
+            want = out + want_x.float().sum(0)
+            K.colsum_cast(x, xf, out, accumulate=True)
+            report(f"colsum_cast {M}x{N} (first {nf} fp32): stored bf16 copy", float((x.float() - want_x.float()).abs().max()), 0.0)
+            report(f"colsum_cast {M}x{N}: sums", rel(out, want), 1e-5)
+            out2 = torch.empty(N, device=dev)
+            K.colsum(x, out2, accumulate=False)
+            report(f"colsum {M}x{N}", rel(out2, want_x.float().sum(0)), 1e-5)
+    run("colsum", f)
+
+
 def probe_ln():
+    probe_colsum()
     def f():
         # M = 12605 / 5003: more row groups than SMs x stages (ring reuse) and a ragged last group
         for D, M in ((768, 1000), (1024, 1000), (512, 1000), (768, 12605), (128, 5003), (1024, 4099)):

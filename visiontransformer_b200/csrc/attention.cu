@@ -75,8 +75,6 @@ __global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
                 const DropCfg drop) {
-  pdl_wait();
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::kBar);
@@ -113,6 +111,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;   // S buffers at columns 0 / 64, O buffers at 128 / 192
+  // on-chip prologue done (barriers, TMEM, descriptor prefetch): it overlapped the previous kernel's tail (PDL)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 8) {
     // ---------------------------------------------------------------- control warp (converged; elected lane issues)
@@ -334,8 +335,6 @@ __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                       __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
                       const DropCfg drop) {
-  pdl_wait();
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdShortSmem::kBar);
@@ -369,6 +368,9 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // on-chip prologue done (barriers, TMEM, descriptor prefetch): it overlapped the previous kernel's tail (PDL)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 8) {
     // ---------------------------------------------------------------- control warp
@@ -599,8 +601,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
                 const __grid_constant__ CUtensorMap tmap_do, const float* __restrict__ lse,
                 const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_accum,
                 int B, int N, int H, float scale, const DropCfg drop) {
-  pdl_wait();
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBar);
@@ -646,6 +646,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // on-chip prologue done (barriers, TMEM, descriptor prefetch): it overlapped the previous kernel's tail (PDL)
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 64, tm_dv = tmem_base + 128, tm_dk = tmem_base + 192,
                  tm_dq = tmem_base;
 
