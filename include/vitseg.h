@@ -189,7 +189,8 @@ int vs_upsample_argmax_stats(const float* low, const int64_t* labels, uint8_t* m
  * into a rounded uint8 intermediate [C,H,Wout], then vertical; 22-bit fixed-point weights.  bounds [out*2] = (first
  * source index, tap count) and coef [out*ksize] int32 per output coordinate come from the host (precompute_coeffs /
  * normalize_coeffs_8bpc restated in visiontransformer_b200/worker.py).  Bit-identical to Pillow for the same pixels.
- *   vs_resample_v_u8 writes dst_f32 = value * scale (ToTensor: scale = 1/255) and/or dst_u8 (either may be NULL).
+ *   vs_resample_v_u8 writes dst_f32 = value / scale (ToTensor: scale = 255, a true division like .div(255)) and/or
+ *   dst_u8 (either may be NULL).
  *   vs_u8_to_f32: ToTensor alone (no resize needed).
  * ------------------------------------------------------------------------------------------------ */
 int vs_resample_h_u8(const uint8_t* src, int64_t row_stride, int64_t plane_stride, int32_t C, int32_t H, int32_t W,

@@ -276,16 +276,18 @@ def learnable_labels(x, num_classes, patch=16):
 
 
 def curve_task(name: str = "regions", B: int = 2, S: int = 224, num_classes: int = 17, block: int = 32,
-               noise: float = 0.5, contrast: float = 0.8):
+               noise: float = 0.5, contrast: float = 0.8, seed: int = 77, palette_seed: int = 77):
     """fixed batch for the 200-step loss-curve parity run (tests/golden/vitb16_curve.pt).
       'regions': block x block pixel cells, each of one class, coloured from a fixed palette (scaled by `contrast`) plus
                  uniform pixel noise; a fraction `noise` of the label pixels is replaced by uniformly random classes, so
                  the loss falls smoothly from ln(17) towards an irreducible floor instead of collapsing to 0 (where a
                  relative gap is meaningless);
       'brightness': the learnable_labels task of the 60-step test."""
-    g = torch.Generator().manual_seed(77)
+    g = torch.Generator().manual_seed(seed)
     if name == "regions":
-        pal = torch.rand(num_classes, 3, generator=g)
+        pal = torch.rand(num_classes, 3, generator=torch.Generator().manual_seed(palette_seed))
+        if seed == palette_seed:
+            torch.rand(num_classes, 3, generator=g)   # keep the stream of the original single-generator version
         z = torch.randint(0, num_classes, (B, S // block, S // block), generator=g)
         z = z.repeat_interleave(block, 1).repeat_interleave(block, 2)
         x = pal[z].permute(0, 3, 1, 2) * contrast + (1.0 - contrast) * torch.rand(B, 3, S, S, generator=g)

@@ -44,7 +44,7 @@ resample_h_kernel(const uint8_t* __restrict__ src, long long row_stride, long lo
 }
 
 // vertical pass: thread per output element (x fastest: coalesced reads of the intermediate rows); writes
-// float(v) * scale (ToTensor: / 255) and/or the uint8 value
+// float(v) / scale (ToTensor: scale = 255) and/or the uint8 value
 __global__ void __launch_bounds__(256)
 resample_v_kernel(const uint8_t* __restrict__ src, int C, int H, int Wout, const int* __restrict__ bounds,
                   const int* __restrict__ coef, int ksize, int Hout, float* __restrict__ dst_f32, float scale,
@@ -62,18 +62,18 @@ resample_v_kernel(const uint8_t* __restrict__ src, int C, int H, int Wout, const
     int ss = 1 << (kPrecisionBits - 1);
     for (int j = 0; j < n; ++j) ss += (int)col[(long long)j * Wout] * k[j];
     const int v = clip8(ss);
-    if (dst_f32 != nullptr) dst_f32[i] = (float)v * scale;
+    if (dst_f32 != nullptr) dst_f32[i] = (float)v / scale;   // a true division, as ToTensor's .div(255)
     if (dst_u8 != nullptr) dst_u8[i] = (uint8_t)v;
   }
 }
 
-// uint8 [C,H,W] -> fp32 [C,H,W] * scale (ToTensor when no resize is needed in either direction)
+// uint8 [C,H,W] -> fp32 [C,H,W] / scale (ToTensor when no resize is needed in either direction)
 __global__ void __launch_bounds__(256)
 u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
   pdl_wait();
   pdl_trigger();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = (float)src[i] * scale;
+    dst[i] = (float)src[i] / scale;
 }
 
 }  // namespace vs

@@ -187,6 +187,71 @@ upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask
   }
 }
 
+// Region form of the fused upsample + argmax (C <= 32): one warp per (image, region), lane = column.  As in the fused
+// cross-entropy, the column-constant part of the bilinear interpolation is hoisted: z_c(y, x) = ly0 * a_c + ly1 * b_c with
+// a_c, b_c in registers, so a pixel costs 2 FMAs + a compare/select pair per class instead of 4 shared-memory reads and
+// ~12 instructions (r01: the fused mask path was SLOWER than writing 218 MB of logits and taking their argmax).
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+upsample_argmax_region_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask, int B, int C, int g, int S) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_cell[8][4][CMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nreg = (long long)B * (g + 1) * (g + 1);
+  const long long rid = (long long)blockIdx.x * 8 + warp;
+  if (rid >= nreg) return;
+  const Region r = region_of(rid, g, S);
+  const float scale = (float)g / (float)S;
+  const int P = S / g;
+  int y0, y1, x0, x1;
+  float t0, t1;
+  bil_coord(r.y_lo, scale, g, y0, y1, t0, t1);
+  bil_coord(r.x_lo, scale, g, x0, x1, t0, t1);
+  const float* lb = low + (long long)r.b * C * g * g;
+  for (int c = lane; c < C; c += 32) {
+    s_cell[warp][0][c] = lb[c * g * g + y0 * g + x0];
+    s_cell[warp][1][c] = lb[c * g * g + y0 * g + x1];
+    s_cell[warp][2][c] = lb[c * g * g + y1 * g + x0];
+    s_cell[warp][3][c] = lb[c * g * g + y1 * g + x1];
+  }
+  __syncwarp();
+  const int xi = lane % P, roff = lane / P, rstep = (32 / P) > 0 ? (32 / P) : 1;
+  const int x = r.x_lo + xi;
+  if (x >= r.x_hi || lane >= P * rstep) return;
+  int q0, q1;
+  float lx0, lx1;
+  bil_coord(x, scale, g, q0, q1, lx0, lx1);
+  float a[CMAX], bq[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    a[c] = 0.0f; bq[c] = 0.0f;
+    if (c < C) {
+      a[c] = lx0 * s_cell[warp][0][c] + lx1 * s_cell[warp][1][c];
+      bq[c] = lx0 * s_cell[warp][2][c] + lx1 * s_cell[warp][3][c];
+    }
+  }
+  uint8_t* out = mask + (long long)r.b * S * S + x;
+  for (int y = r.y_lo + roff; y < r.y_hi; y += rstep) {
+    float ly0, ly1;
+    bil_coord(y, scale, g, q0, q1, ly0, ly1);
+    int bi = 0;
+    if (CMAX == 1) {
+      bi = (ly0 * a[0] + ly1 * bq[0]) > 0.0f ? 1 : 0;
+    } else {
+      float best = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          const float v = ly0 * a[c] + ly1 * bq[c];
+          if (v > best) { best = v; bi = c; }
+        }
+      }
+    }
+    out[(long long)y * S] = (uint8_t)bi;
+  }
+}
+
 // class map -> colour image through the class palette: colored_pred = index_to_color[pred_labels]
 // (model/CE/testViTModel.py:139-143; the mask_image the worker posts back, backend/core/views.py:116-149).
 // uint8 [n] class ids -> uint8 [n, 3] RGB; 4 pixels (12 output bytes = three 32-bit words) per thread.
@@ -940,6 +1005,17 @@ extern "C" int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, in
   VS_CHECK_ARG(low && mask, "vs_upsample_argmax: null pointer");
   if (int rc = check_grid("vs_upsample_argmax", B, C, g, S)) return rc;
   VS_CHECK_ARG(C <= 255, "vs_upsample_argmax: C must be <= 255");
+  if (C <= 32) {
+    const long long nreg = (long long)B * (g + 1) * (g + 1);
+    const unsigned grid = (unsigned)((nreg + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 1) launch_k(upsample_argmax_region_kernel<1>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
+    else if (C <= 8) launch_k(upsample_argmax_region_kernel<8>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
+    else if (C <= 17) launch_k(upsample_argmax_region_kernel<17>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
+    else launch_k(upsample_argmax_region_kernel<32>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
+    VS_CHECK_LAUNCH();
+    return 0;
+  }
   int chunks;
   size_t smem;
   if (int rc = plan_image_chunks("vs_upsample_argmax", B, C, g, S, S / 8, &chunks, &smem)) return rc;

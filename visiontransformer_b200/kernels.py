@@ -354,8 +354,8 @@ def resample_h(src, bounds, coef, ksize, wout, dst):
     return dst
 
 
-def resample_v(src, bounds, coef, ksize, hout, dst_f32=None, scale=1.0 / 255.0, dst_u8=None):
-    """uint8 [C,H,W] contiguous -> [C,hout,W]: Pillow's vertical pass; fp32 (value * scale) and/or uint8 output."""
+def resample_v(src, bounds, coef, ksize, hout, dst_f32=None, scale=255.0, dst_u8=None):
+    """uint8 [C,H,W] contiguous -> [C,hout,W]: Pillow's vertical pass; fp32 (value / scale) and/or uint8 output."""
     require_cuda(src, "resample_v")
     assert src.dtype == torch.uint8 and src.is_contiguous()
     Cn, H, W = src.shape
@@ -364,7 +364,7 @@ def resample_v(src, bounds, coef, ksize, hout, dst_f32=None, scale=1.0 / 255.0, 
                                        ptr(dst_u8), stream()), "vs_resample_v_u8")
 
 
-def u8_to_f32(src, dst, scale=1.0 / 255.0):
+def u8_to_f32(src, dst, scale=255.0):
     require_cuda(src, "u8_to_f32")
     assert src.dtype == torch.uint8 and src.is_contiguous() and dst.dtype == F32 and dst.is_contiguous()
     _count(1)
