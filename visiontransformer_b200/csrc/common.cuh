@@ -41,6 +41,9 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // same with an explicit swizzle span in bytes (128, 64, 32 or 0 = none); box[0] * 2 must not exceed it
 int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+// general form: elem_bytes 2 (bf16) or 4 (fp32)
+int make_tmap_sw(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------

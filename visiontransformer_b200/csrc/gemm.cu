@@ -55,6 +55,9 @@ struct GemmParams {
 // EPI = 1: bf16 outputs leave through shared memory and cp.async.bulk.tensor stores: each epilogue warp owns one
 //          swizzled [32 rows x BN/4 columns] bf16 staging tile (4 KB for BN = 256), which also receives the GELU' / ReLU
 //          mask operand (aux) by TMA load ahead of the accumulator.
+// EPI = 2: fp32 outputs (+ fp32 residual) of the 128-column tiles: two [32 x 32] fp32 tiles (128-byte rows) per warp; the
+//          residual tile of the NEXT work item is fetched by TMA while the current one is processed, results are added in
+//          place and leave by TMA store.
 template <int BN, int CTA2, int EPI>
 struct Cfg {
   static constexpr int kBNH = CTA2 ? BN / 2 : BN;                // B rows staged per CTA
@@ -62,9 +65,9 @@ struct Cfg {
   static constexpr int kABytes = BM * BK * 2;                    // 16 KB
   static constexpr int kBAlloc = kBBoxes * 64 * BK * 2;          // smem reserved for B per stage
   static constexpr int kStageBytes = kABytes + kBAlloc;
-  static constexpr int kEpiWarpBytes = EPI ? (BN / 4) * 32 * 2 : 2048;   // per-warp staging tile
+  static constexpr int kEpiWarpBytes = EPI == 1 ? (BN / 4) * 32 * 2 : (EPI == 2 ? 2 * 4096 : 2048);   // per-warp staging
   static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
-  static constexpr int kBarBytes = 512;
+  static constexpr int kBarBytes = 1024;
   static constexpr int kBudget = 227 * 1024 - kBarBytes - 1024 - kEpiBytes;   // 1024: manual alignment slack
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kEpiOffset = kStages * kStageBytes;
@@ -515,6 +518,100 @@ __device__ __forceinline__ void epilogue_tile_bf16_tma(const GemmParams& p, cons
   }
 }
 
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// fp32 epilogue through shared memory + TMA (EPI = 2, 128-column tiles: a warp's 32 columns are one 128-byte row).
+// out = dropout(act(acc + bias)) + residual.  The register-direct / transposed form reads the fp32 residual with LSU
+// loads issued one 16-column chunk ahead of their use: with K = 768 the residual stream, not the MMA, bounded the
+// out-projection GEMM (r02 breakdown: 40 us for 15 GFLOP = 369 TFLOP/s).  Here the residual tile of the NEXT work item is
+// already in shared memory when its accumulator completes (TMA load issued one tile ahead into the other of two
+// buffers); thread = row adds its 32 values in place (swizzled 16-byte accesses, conflict-free) and one TMA store writes
+// the tile.
+// ------------------------------------------------------------------------------------------------
+template <int kChunks>
+__device__ __forceinline__ void epilogue_tile_f32_tma(const GemmParams& p, const CUtensorMap* tm_out, uint8_t* buf,
+                                                      uint64_t* res_bar, uint32_t res_phase, uint32_t tmem_addr,
+                                                      uint64_t* tfull, uint32_t tfull_phase, int row0, int col0,
+                                                      int lane) {
+  static_assert(kChunks == 2, "EPI = 2 is defined for 128-column tiles (32 fp32 columns per warp)");
+  const bool add_bias = p.bias != nullptr;
+  const bool use_res = p.residual != nullptr;
+  u32x8 bs[2][2];
+  auto prefetch = [&](int c, int b) {
+    const int n = col0 + c * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bs[b][0].v[j] = 0u; bs[b][1].v[j] = 0u; }
+    if (add_bias && n < p.N) {
+      bs[b][0] = ld_global_nc_256(p.bias + n);
+      bs[b][1] = ld_global_nc_256(p.bias + n + 8);
+    }
+  };
+  prefetch(0, 0);
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  if (use_res) {
+    mbar_wait(res_bar, res_phase);
+  } else {
+    if (lane == 0) bulk_wait_read1();   // this buffer's previous store (two tiles ago) has drained
+    __syncwarp();
+  }
+  uint32_t v[16];
+  tmem_ld16(tmem_addr, v);
+  const uint32_t dseed = p.drop.thresh != 0u ? drop_seed(p.drop) : 0u;
+  const int r = row0 + lane;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int n = col0 + c * 16;
+    tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    if (c + 1 < kChunks) {
+      tmem_ld16(tmem_addr + (c + 1) * 16, v);
+      prefetch(c + 1, (c + 1) & 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] += __uint_as_float(bs[c & 1][0].v[j]);
+      f[8 + j] += __uint_as_float(bs[c & 1][1].v[j]);
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+    if (p.drop.thresh != 0u) {   // TF:267 / TF:310: dropout(dense(x)) then + residual; same element -> mask map as EPI 0
+      const uint32_t e = (uint32_t)r * (uint32_t)p.N + (uint32_t)n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bool k0, k1;
+        drop_keep2(e + 2 * j, dseed, p.drop.thresh, k0, k1);
+        f[2 * j] = k0 ? f[2 * j] * p.drop.scale : 0.0f;
+        f[2 * j + 1] = k1 ? f[2 * j + 1] * p.drop.scale : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4* slot = reinterpret_cast<float4*>(buf + lane * 128 + (((4 * c + q) ^ (lane & 7)) << 4));
+      float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      if (use_res) {
+        const float4 rr = *slot;
+        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+      }
+      *slot = o;
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && row0 < p.M && col0 < p.N) {
+    tma_store_2d(tm_out, buf, col0, row0);
+    bulk_commit();
+  }
+}
+
 template <int BN, int A_MN, int B_MN, int CTA2, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -530,7 +627,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* aux_bar = tempty_bar + 2;           // one per epilogue warp (EPI = 1 with an aux operand)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * kEpiWarps);
   SchedSmem* ss = reinterpret_cast<SchedSmem*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);
 
   const int warp = threadIdx.x >> 5;
@@ -545,7 +642,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (EPI) {
       tma_prefetch_desc(&tmap_out);
       if (p.out2 != nullptr) tma_prefetch_desc(&tmap_out2);
-      if (p.aux_mode != 0) tma_prefetch_desc(&tmap_aux);
+      if (p.aux_mode != 0 || (EPI == 2 && p.residual != nullptr)) tma_prefetch_desc(&tmap_aux);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -558,7 +655,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&tempty_bar[i], kEpiWarps * kNCta);
     }
     if (EPI) {
-      for (int i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     }
     for (int i = 0; i < kSched; ++i) {
       mbar_init(&ss->full[i], 1);
@@ -727,27 +824,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_expect_tx(&aux_bar[ew], L::kEpiWarpBytes);
       tma_load_2d(stg, &tmap_aux, &aux_bar[ew], c0, r0);
     };
-    if (EPI && p.aux_mode != 0 && lane == 0) load_aux(unit);
-    int w_next = ti.next(unit, lane);   // one work item ahead: the aux tile of the next item is prefetched
-    for (int w = unit; w >= 0; w = w_next, w_next = (w >= 0 ? ti.next(w, lane) : -1)) {
+    auto load_res = [&](int w, int b) {   // lane 0 (EPI = 2): fp32 residual tile of work item w -> buffer b
+      int r0, c0;
+      tile_origin(w, r0, c0);
+      mbar_expect_tx(&aux_bar[2 * ew + b], 4096);
+      tma_load_2d(stg + b * 4096, &tmap_aux, &aux_bar[2 * ew + b], c0, r0);
+    };
+    const bool res_tma = EPI == 2 && p.residual != nullptr;
+    if (EPI == 1 && p.aux_mode != 0 && lane == 0) load_aux(unit);
+    if (res_tma && lane == 0) load_res(unit, 0);
+    int w_next = ti.next(unit, lane);   // one work item ahead: the aux / residual tile of the next item is prefetched
+    int ntile = 0;
+    for (int w = unit; w >= 0; w = w_next, w_next = (w >= 0 ? ti.next(w, lane) : -1), ++ntile) {
       const int split = w / tiles;
       int row0, col0;
       tile_origin(w, row0, col0);
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + slice * kColsPerWarp);
-      if constexpr (EPI != 0)
+      if constexpr (EPI == 2) {
+        const int b = ntile & 1;
+        if (res_tma && lane == 0 && w_next >= 0) {
+          bulk_wait_read0();            // the previous tile's store out of the other buffer has drained it
+          load_res(w_next, b ^ 1);      // lands while this tile is processed
+        }
+        epilogue_tile_f32_tma<kChunks>(p, &tmap_out, stg + b * 4096, &aux_bar[2 * ew + b], (uint32_t)(ntile >> 1) & 1u, taddr,
+                                       &tfull_bar[acc], acc_phase, row0, col0, lane);
+      } else if constexpr (EPI == 1) {
         epilogue_tile_bf16_tma<kChunks>(p, &tmap_out, &tmap_out2, stg, &aux_bar[ew], aux_phase, taddr, &tfull_bar[acc],
                                         acc_phase, row0, col0, split == 0, lane);
-      else if (p.out_f32)
+      } else if (p.out_f32) {
         epilogue_tile_f32<kChunks>(p, stg, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
-      else
+      } else {
         epilogue_tile_bf16<kChunks>(p, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CTA2 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0);
         else mbar_arrive_relaxed(&tempty_bar[acc]);
       }
-      if (EPI && p.aux_mode != 0) {
+      if (EPI == 1 && p.aux_mode != 0) {
         aux_phase ^= 1;
         if (lane == 0 && w_next >= 0) {
           bulk_wait_read0();          // the store issued above has drained the buffer
@@ -815,7 +930,10 @@ static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtenso
 template <int BN, int CTA2>
 static int launch_epi(int epi, int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om,
                       const GemmParams& p, int grid, cudaStream_t st) {
-  if (epi) return launch_major<BN, CTA2, 1>(a_mn, b_mn, ta, tb, om, p, grid, st);
+  if (epi == 1) return launch_major<BN, CTA2, 1>(a_mn, b_mn, ta, tb, om, p, grid, st);
+  if constexpr (BN == 128) {
+    if (epi == 2) return launch_major<BN, CTA2, 2>(a_mn, b_mn, ta, tb, om, p, grid, st);
+  }
   return launch_major<BN, CTA2, 0>(a_mn, b_mn, ta, tb, om, p, grid, st);
 }
 
@@ -919,7 +1037,10 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   }
   const bool want_tma = epi_env == 1 && d->out_dtype == 0;
   TileChoice tc = choose_tiles(d->M, d->N, p.kblocks, nsm, d->accumulate != 0, d->split_k, forced_cfg, !want_tma);
-  const int epi = (want_tma && tc.bn != 192) ? 1 : 0;
+  // fp32 outputs (+ residual) of the 128-column tiles: TMA residual prefetch + TMA store (EPI = 2)
+  const bool f32_tma = epi_env == 1 && d->out_dtype == 1 && !d->accumulate && d->row_tokens == 0 && tc.bn == 128 &&
+                       d->aux_mode == 0 && d->out2 == nullptr && d->ldo % 4 == 0 && (d->residual == nullptr || d->ldr % 4 == 0);
+  const int epi = (want_tma && tc.bn != 192) ? 1 : (f32_tma ? 2 : 0);
   int splits = tc.splits;
   if (splits > p.kblocks) splits = p.kblocks;
   // every split must own at least one k-block
@@ -962,7 +1083,18 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   }
   OutMaps om;
   om.out = ta; om.out2 = ta; om.aux = ta;   // placeholders (never dereferenced) unless EPI = 1
-  if (epi) {
+  if (epi == 2) {
+    uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M}, strides[1];
+    uint32_t box[2] = {32u, 32u};
+    strides[0] = (uint64_t)d->ldo * 4;
+    int rc = make_tmap_sw(&om.out, d->out, 4, 2, dims, strides, box, 128);
+    if (rc) return rc;
+    if (d->residual) {
+      strides[0] = (uint64_t)d->ldr * 4;
+      rc = make_tmap_sw(&om.aux, d->residual, 4, 2, dims, strides, box, 128);
+      if (rc) return rc;
+    }
+  } else if (epi) {
     // one [32 rows x BN/4 columns] box per epilogue warp; 128-byte rows (BN = 256) or 64-byte rows (BN = 128)
     uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M}, strides[1];
     uint32_t box[2] = {(uint32_t)(BN / 4), 32u};

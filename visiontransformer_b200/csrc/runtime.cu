@@ -62,6 +62,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, int swizzle_bytes) {
+  return make_tmap_sw(out, base, 2, rank, dims, strides_bytes, box, swizzle_bytes);
+}
+
+int make_tmap_sw(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                               : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
@@ -73,7 +79,7 @@ int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
