@@ -304,6 +304,10 @@ def library_baseline(cfg, dev, B, steps=5, warmup=3):
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     logits = m(batch[0])
                 logits = logits.float()
+                with torch.device(dev):   # the loss restatements build their small constant kernels with torch.tensor(...)
+                    _loss_and_step(logits)
+
+            def _loss_and_step(logits):
                 if cfg["wrapper"] == "ce":
                     loss = F.cross_entropy(logits, O.resize_target(batch[1], S))
                 elif cfg["wrapper"] == "paed_multi":
@@ -352,6 +356,9 @@ def dp_check(dev, rank, world):
         with torch.no_grad():                        # a head with real signal (torch's default init is tiny)
             for p in m.model.seg_head.parameters():
                 p.mul_(4.0)
+            for p in m.parameters():                 # non-zero biases: a relative error needs a non-zero reference
+                if p.dim() == 1:
+                    p.add_(0.02 * torch.randn_like(p))
         return m.to(dev).train()
 
     def compare(cls, C, batch, steps=2):
@@ -682,6 +689,11 @@ def run_ours(args, cfg):
                 "l2": "working set per step (activations + weights, GBs) >> 126 MB L2; no flush needed"}
         if train:
             conf["optimizer"] = opt_name + " in timed region"
+            if world > 1:
+                conf["grad_allreduce"] = {"multimem": "in-switch (NVLS) reduction by vs_multimem_allreduce_f32, one co-resident CTA per SM, bucketed and overlapped with backward",
+                                          "nccl": "bucketed NCCL all-reduce overlapped with backward"}.get(dp.reduce_backend, dp.reduce_backend)
+                if dp.reduce_fallback_reason:
+                    conf["grad_allreduce_fallback"] = dp.reduce_fallback_reason[:200]
             if cfg["wrapper"] != "paed_bin":
                 conf["label_resize"] = "256 -> image-size nearest inside the step, as LightningViTModel.training_step"
         else:

@@ -183,6 +183,16 @@ int vs_upsample_argmax_stats(const float* low, const int64_t* labels, uint8_t* m
                              int32_t C, int32_t g, int32_t S, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Data-parallel gradient all-reduce in the NVSwitch (net-new: the reference trains on one device,
+ * model/CE/createViTmodel.py:72-73).  multicast_ptr = multicast (NVLS) address of n fp32 elements of a buffer that
+ * every rank allocated symmetrically; on return of the kernel this rank's 1/world slice holds scale * (sum over ranks)
+ * on EVERY rank (multimem.ld_reduce + multimem.st).  All ranks must call it for the same range, bracketed by
+ * cross-GPU barriers (done by visiontransformer_b200/dp.py).  One 128-thread, <= 32-register CTA per SM: sized to be
+ * resident next to a tcgen05 GEMM CTA instead of displacing it.
+ * ------------------------------------------------------------------------------------------------ */
+int vs_multimem_allreduce_f32(void* multicast_ptr, int64_t n, int32_t rank, int32_t world, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Worker-side pre-processing: Pillow's Image.resize(size, BILINEAR) — what
  * transforms.Resize((224, 224)) does to the PIL image at model/CE/testViTModel.py:92-97 — followed by ToTensor, on
  * planar uint8 [C,H,W] device images (the layout nvJPEG delivers).  Two passes as in libImaging/Resample.c: horizontal

@@ -73,7 +73,11 @@ if rank == 0:
     adam = [i for i, e in enumerate(evs) if "adam_kernel" in e.name]
     lo, hi = (adam[0] + 1, adam[1] + 1) if len(adam) >= 2 else (0, len(evs))
     step_evs = evs[lo:hi]
-    nccl = [(e.time_range.start, e.time_range.end) for e in step_evs if "nccl" in e.name.lower()]
+    def is_comm(name):
+        n = name.lower()
+        return "nccl" in n or "multimem_allreduce" in n or "barrier" in n
+
+    nccl = [(e.time_range.start, e.time_range.end) for e in step_evs if is_comm(e.name)]
     t0 = step_evs[0].time_range.start
     with open(args.out, "w", newline="") as f:
         w = csv.writer(f)
@@ -81,7 +85,7 @@ if rank == 0:
         k = 0
         for e in step_evs:
             s, t = e.time_range.start, e.time_range.end
-            is_nccl = "nccl" in e.name.lower()
+            is_nccl = is_comm(e.name)
             ov = any(s < b and a < t for a, b in nccl) and not is_nccl
             w.writerow([-1 if is_nccl else k, e.name[:120], f"{s - t0:.1f}", f"{t - s:.2f}", int(ov)])
             k += 0 if is_nccl else 1

@@ -21,7 +21,8 @@ def family(name):
     m = re.search(r"vs::(\w+)", name)
     if m:
         return m.group(1)
-    return "nccl" if "nccl" in name.lower() else "torch glue"
+    n = name.lower()
+    return "comm" if ("nccl" in n or "barrier" in n) else "torch glue"
 
 
 a, b = load(sys.argv[1]), load(sys.argv[2])

@@ -65,6 +65,7 @@ _SIGS = {
     "vs_resample_v_u8": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p,
                          c_void_p],
     "vs_u8_to_f32": [c_void_p, c_void_p, c_i64, c_float, c_void_p],
+    "vs_multimem_allreduce_f32": [c_void_p, c_i64, c_int, c_int, c_float, c_void_p],
     "vs_sdf_workspace_bytes": [c_int, c_int],
     "vs_sdf_targets": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "vs_upsample_ce": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -280,7 +280,7 @@ conv1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
                    int F, int C) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float s_dl[64][kMaxClasses];
+  __shared__ __align__(16) float s_dl[kMaxClasses][64];   // class-major: one LDS.128 = the gradients of 4 pixels
   __shared__ __align__(16) __nv_bfloat16 s_x[64][256];   // feature rows of the current pixel group (F <= 256)
   const int f = threadIdx.x;
   const long long npix = (long long)B * T;
@@ -296,39 +296,53 @@ conv1x1_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __res
   for (long long base = p0; base < p1; base += 64) {
     const int n = int(min((long long)64, p1 - base));
     __syncthreads();
-    for (int i = threadIdx.x; i < n * C; i += blockDim.x) {
-      const int pi = i / C, c = i - pi * C;
-      const long long pix = base + pi;
-      const int b = int(pix / T), t = int(pix - (long long)b * T);
-      s_dl[pi][c] = dlogits[((long long)b * C + c) * T + t];
+    for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) {
+      const int c = i / 64, pi = i - c * 64;
+      float v = 0.0f;   // pixels beyond n contribute zero (the loop below runs in groups of 4)
+      if (pi < n) {
+        const long long pix = base + pi;
+        const int b = int(pix / T), t = int(pix - (long long)b * T);
+        v = dlogits[((long long)b * C + c) * T + t];
+      }
+      s_dl[c][pi] = v;
     }
     // all feature rows of the group in flight at once (16-byte loads) instead of one dependent 2-byte load per pixel
     // and thread: the kernel was latency-bound (100 us for 6.4 MB, ncu r01)
     if ((F & 7) == 0) {
       const int f8 = F >> 3;
-      for (int i = threadIdx.x; i < n * f8; i += blockDim.x) {
+      for (int i = threadIdx.x; i < 64 * f8; i += blockDim.x) {
         const int pi = i / f8, q = i - pi * f8;
-        *reinterpret_cast<uint4*>(&s_x[pi][q * 8]) = *reinterpret_cast<const uint4*>(feat + (base + pi) * F + q * 8);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (pi < n) v = *reinterpret_cast<const uint4*>(feat + (base + pi) * F + q * 8);
+        *reinterpret_cast<uint4*>(&s_x[pi][q * 8]) = v;
       }
     } else {
-      for (int i = threadIdx.x; i < n * F; i += blockDim.x) s_x[i / F][i % F] = feat[(base + i / F) * F + i % F];
+      for (int i = threadIdx.x; i < 64 * F; i += blockDim.x) {
+        const int pi = i / F, ff = i % F;
+        s_x[pi][ff] = pi < n ? feat[(base + pi) * F + ff] : __float2bfloat16(0.0f);
+      }
     }
     __syncthreads();
     if (f < C)
-      for (int pi = 0; pi < n; ++pi) dbacc += s_dl[pi][f];
+      for (int pi = 0; pi < n; ++pi) dbacc += s_dl[f][pi];
     if (f < F) {
-      for (int pi = 0; pi < n; ++pi) {
-        const float x = __bfloat162float(s_x[pi][f]);
-        float d = 0.0f;
+      // four pixels per iteration: independent FMA chains, and the four gradients of a class arrive in one LDS.128
+      for (int pi = 0; pi < n; pi += 4) {
+        float x[4], d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = __bfloat162float(s_x[pi + u][f]);
 #pragma unroll
         for (int c = 0; c < kMaxClasses; ++c) {
           if (c < C) {
-            const float g = s_dl[pi][c];
-            d += g * wc[c];
-            acc[c] += g * x;
+            const float4 g = *reinterpret_cast<const float4*>(&s_dl[c][pi]);
+            d[0] = fmaf(g.x, wc[c], d[0]); d[1] = fmaf(g.y, wc[c], d[1]);
+            d[2] = fmaf(g.z, wc[c], d[2]); d[3] = fmaf(g.w, wc[c], d[3]);
+            acc[c] = fmaf(g.x, x[0], fmaf(g.y, x[1], fmaf(g.z, x[2], fmaf(g.w, x[3], acc[c]))));
           }
         }
-        dfeat[(base + pi) * F + f] = __float2bfloat16(x > 0.0f ? d : 0.0f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (pi + u < n) dfeat[(base + pi + u) * F + f] = __float2bfloat16(x[u] > 0.0f ? d[u] : 0.0f);
       }
     }
   }

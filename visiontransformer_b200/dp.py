@@ -8,6 +8,7 @@ plus a 6-scalar all-reduce inside the PAEDTrainer loss for exact global-batch Di
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -58,6 +59,58 @@ class BucketReducer:
             raise RuntimeError(f"gradient buckets never reduced: {missing}")
 
 
+class MultimemReducer:
+    """Same interface as BucketReducer, but the reduction happens in the NVSwitch (NVLS) through the library's own
+    kernel (csrc/collective.cu) instead of NCCL: the gradient arena lives in symmetric memory; when a bucket is
+    final the communication stream waits for it, passes a cross-GPU barrier, runs vs_multimem_allreduce_f32 on the
+    bucket (one small CTA per SM, resident NEXT TO the backward GEMM CTAs rather than displacing them) and passes a
+    second barrier.  Requires NVLink multicast support (NVSwitch systems); DataParallel falls back to NCCL otherwise."""
+
+    def __init__(self, engine, group=None, average: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.average = average
+        dev = engine.grads.device
+        n = engine.grads.numel()
+        self.buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
+        self.mc_ptr = int(self.hdl.multicast_ptr)
+        if self.mc_ptr == 0:
+            raise RuntimeError("NVLink multicast (NVLS) is not available: the symmetric-memory rendezvous returned no "
+                               "multicast address")
+        engine.set_grad_arena(self.buf)
+        self.flat = self.buf
+        self.ranges = {name: (s, e) for name, s, e in engine.bucket_ranges()}
+        self.order = [name for name, _, _ in engine.bucket_ranges()]
+        self.stream = torch.cuda.Stream(device=dev)
+        self._done: List[str] = []
+
+    def ready(self, name: str):
+        s, e = self.ranges[name]
+        if e <= s:
+            return
+        from . import kernels as K
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)          # this rank's bucket is final
+            self.hdl.barrier(channel=0)         # ... and so is every other rank's
+            K.multimem_allreduce(self.mc_ptr + 4 * s, e - s, self.rank, self.world,
+                                 1.0 / self.world if self.average else 1.0)
+            self.hdl.barrier(channel=0)         # every slice of the bucket has been written back everywhere
+        self._done.append(name)
+
+    def finish(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+        missing = [n for n in self.order if n not in self._done and self.ranges[n][1] > self.ranges[n][0]]
+        self._done = []
+        if missing:
+            raise RuntimeError(f"gradient buckets never reduced: {missing}")
+
+
 def shard_batch(batch, rank: int, world: int):
     """Even split of every tensor of a batch along dim 0 (images are independent: no BatchNorm, per-token LN)."""
     out = []
@@ -88,8 +141,13 @@ class DataParallel:
         if self._global_loss:
             module.dp_group = group
             module.dp_world_size = self.world
-        self._reducer: Optional[BucketReducer] = None
+        self._reducer = None
         self._synced = False
+        # gradient exchange: "multimem" = in-switch reduction by the library's own co-resident kernel (NVLS), "nccl" =
+        # bucketed dist.all_reduce; "auto" tries multimem on NCCL/CUDA process groups and falls back to NCCL
+        self.reduce_mode = os.environ.get("VS_DP_REDUCE", "auto")
+        self.reduce_backend = None
+        self.reduce_fallback_reason = None
 
     def _engine(self):
         return self.module.model.engine
@@ -104,10 +162,24 @@ class DataParallel:
         eng._dirty = True
         self._synced = True
 
+    def _make_reducer(self, eng):
+        backend = dist.get_backend(self.group) if dist.is_initialized() else ""
+        if self.world > 1 and self.reduce_mode in ("auto", "multimem") and backend == "nccl" and eng.grads.is_cuda:
+            try:
+                r = MultimemReducer(eng, self.group, average=not self._global_loss)
+                self.reduce_backend = "multimem"
+                return r
+            except Exception as e:  # noqa: BLE001  (no NVSwitch multicast, old driver, ...)
+                if self.reduce_mode == "multimem":
+                    raise
+                self.reduce_fallback_reason = f"{type(e).__name__}: {e}"
+        self.reduce_backend = "nccl" if backend == "nccl" else backend
+        return BucketReducer(eng.grads, eng.bucket_ranges(), self.group, average=not self._global_loss)
+
     def _attach(self):
         eng = self._engine()
         if self._reducer is None or self._reducer.flat.data_ptr() != eng.grads.data_ptr():
-            self._reducer = BucketReducer(eng.grads, eng.bucket_ranges(), self.group, average=not self._global_loss)
+            self._reducer = self._make_reducer(eng)
         eng.grad_ready_hook = self._reducer.ready if self.world > 1 else None
 
     def step(self, batch, batch_idx: int = 0, sync_grads: bool = True):

@@ -139,6 +139,17 @@ class Engine:
         self._versions = None
         self._ws = {}
 
+    def set_grad_arena(self, buf: torch.Tensor) -> None:
+        """Re-homes the flat gradient arena into `buf` (same size, fp32, same device) — used by the data-parallel
+        wrapper to place it in NVLink symmetric memory.  param.grad views are dropped and re-attached by the next
+        backward."""
+        assert buf.dtype == F32 and buf.numel() == self.grads.numel() and buf.device == self.grads.device
+        buf.copy_(self.grads)
+        self.grads = buf
+        for p in self.module.parameters():
+            p.grad = None
+        self._grads_zeroed = False
+
     def refresh_shadow(self, train: bool = False):
         """fp32 master arena -> bf16 shadow (+ packed head conv weight).
 

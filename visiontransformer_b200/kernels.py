@@ -371,6 +371,12 @@ def u8_to_f32(src, dst, scale=255.0):
     check(_lib.load().vs_u8_to_f32(ptr(src), ptr(dst), src.numel(), scale, stream()), "vs_u8_to_f32")
 
 
+def multimem_allreduce(multicast_ptr: int, n: int, rank: int, world: int, scale: float):
+    """in-switch all-reduce of n fp32 elements at a multicast (NVLS) address: this rank's 1/world slice (dp.py)."""
+    _count(1)
+    check(_lib.load().vs_multimem_allreduce_f32(multicast_ptr, n, rank, world, scale, stream()), "vs_multimem_allreduce_f32")
+
+
 def sdf_targets(mask):
     """mask fp32 [B,S,S] (object > 0.5) -> (sdf_ext, sdf_int) fp32 [B,S,S]: compute_sdf of every image, on the device."""
     require_cuda(mask, "sdf_targets")
