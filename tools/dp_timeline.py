@@ -89,6 +89,11 @@ if rank == 0:
             ov = any(s < b and a < t for a, b in nccl) and not is_nccl
             w.writerow([-1 if is_nccl else k, e.name[:120], f"{s - t0:.1f}", f"{t - s:.2f}", int(ov)])
             k += 0 if is_nccl else 1
+    # bubble between consecutive graph replays: end of a step's optimizer kernel -> start of the next step's first kernel
+    gaps = [evs[i + 1].time_range.start - evs[i].time_range.end for i in adam if i + 1 < len(evs)]
+    intra = sum(max(0.0, b.time_range.start - a.time_range.end) for a, b in zip(step_evs[:-1], step_evs[1:]) if not is_comm(a.name) and not is_comm(b.name))
+    print(f"rank 0: gap between steps (optimizer end -> next step's first kernel): {[round(g, 1) for g in gaps]} us; sum of the "
+          f"gaps between consecutive compute kernels inside the step: {intra:.0f} us", file=sys.stderr)
     span = step_evs[-1].time_range.end - t0
     print(f"rank 0: {len(step_evs)} kernels in the profiled step, {len(nccl)} NCCL kernels, span {span / 1e3:.3f} ms -> {args.out}",
           file=sys.stderr)

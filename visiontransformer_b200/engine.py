@@ -17,6 +17,7 @@ Data layout in HBM
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -87,6 +88,8 @@ class Engine:
         self.rng_step = None         # device uint32 counter: advances once per dropout-enabled forward (graph-safe)
         self._drop = (0.0, 0.0)      # (hidden p, attention p) used by the last training forward
         self.launches = 0            # kernel launches issued by the last forward/backward (for bench bookkeeping)
+        self._two_streams = os.environ.get("VS_BWD_STREAMS", "2") != "1"
+        self._side = None
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -138,6 +141,11 @@ class Engine:
         self.head_wgrad_packed = torch.zeros(HEAD_CH, 9 * D, device=device, dtype=F32)
         self._versions = None
         self._ws = {}
+
+    def _side_stream(self):
+        if self._side is None or self._side.device != self.device:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def set_grad_arena(self, buf: torch.Tensor) -> None:
         """Re-homes the flat gradient arena into `buf` (same size, fp32, same device) — used by the data-parallel
@@ -433,29 +441,57 @@ class Engine:
         if hook:
             hook("head")
         # --- encoder layers in reverse
+        # Weight-gradient GEMMs run on a second stream, concurrently with the data-gradient chain: dW = dY^T X and
+        # dX = dY W are independent, and at batch 64 every GEMM ends in a partly filled wave (12608 rows = 49.25 tiles
+        # of 256) — the other kernel's CTAs fill the SMs that a kernel's tail wave leaves idle.  Forks / joins are
+        # events, so the pattern is captured into the step's CUDA graph as parallel branches.  VS_BWD_STREAMS=1 keeps
+        # everything on one stream.
+        side = self._side_stream() if self._two_streams else None
+        cur = torch.cuda.current_stream()
+
+        def fork():   # side stream continues from the current point of the main stream
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+
+        def join():   # main stream waits for everything queued on the side stream
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                cur.wait_event(ev)
+
+        def wgrad(dy, xsaved, gw):
+            if side is None:
+                K.gemm(dy, xsaved, gw, a_mn=True, b_mn=True, accumulate=True)
+            else:
+                with torch.cuda.stream(side):
+                    K.gemm(dy, xsaved, gw, a_mn=True, b_mn=True, accumulate=True)
+
         for i in reversed(range(L)):
             p = f"backbone.encoder.layer.{i}."
             st = ws["stats"][i]
             # fc2: x_out = x_mid + h_act W2^T + b2   (its bias gradient = column sums of dx16: fused into the
             # LayerNorm backward that produced dx16)
-            K.gemm(ws["dx16"], ws["h_act"][i], self.g32(p + "output.dense.weight"), a_mn=True, b_mn=True,
-                   accumulate=True)
+            fork()
+            wgrad(ws["dx16"], ws["h_act"][i], self.g32(p + "output.dense.weight"))
             K.gemm(ws["dx16"], self.w16(p + "output.dense.weight"), ws["dh"], b_mn=True, aux=ws["h_pre"][i],
                    aux_mode=K.AUX_GELU_GRAD)
             # fc1
+            fork()   # dh is final
+            wgrad(ws["dh"], ws["ln2"][i], self.g32(p + "intermediate.dense.weight"))
             K.colsum(ws["dh"], self.g32(p + "intermediate.dense.bias"), accumulate=True)
-            K.gemm(ws["dh"], ws["ln2"][i], self.g32(p + "intermediate.dense.weight"), a_mn=True, b_mn=True,
-                   accumulate=True)
             K.gemm(ws["dh"], self.w16(p + "intermediate.dense.weight"), ws["d_ln"], b_mn=True)
-            # LN2 + skip
+            # LN2 + skip (overwrites dx16, which the fc2 weight gradient reads: join first)
+            join()
             K.layernorm_bwd(ws["d_ln"], ws["x_mid"][i], self.w32(p + "layernorm_after.weight"), st[2], st[3], dx,
                             dx_other, ws["dx16"], self.g32(p + "layernorm_after.weight"),
                             self.g32(p + "layernorm_after.bias"), dropout=self._site(p_hid, 1 + 2 * i),
                             dbias=self.g32(p + "attention.output.dense.bias"))
             dx, dx_other = dx_other, dx
             # attention output projection
-            K.gemm(ws["dx16"], ws["ctx"][i], self.g32(p + "attention.output.dense.weight"), a_mn=True, b_mn=True,
-                   accumulate=True)
+            fork()
+            wgrad(ws["dx16"], ws["ctx"][i], self.g32(p + "attention.output.dense.weight"))
             K.gemm(ws["dx16"], self.w16(p + "attention.output.dense.weight"), ws["dctx"], b_mn=True)
             # attention core
             K.attention_bwd(ws["qkv"][i], ws["ctx"][i], ws["dctx"], ws["lse"][i], ws["dqkv"], ws["dq_acc"], ws["delta"],
@@ -465,10 +501,12 @@ class Engine:
             gw, gb = self.fused_qkv(i, arena="grads")
             wqkv, _ = self.fused_qkv(i)
             K.colsum_cast(ws["dqkv"], ws["dq_acc"], gb, accumulate=True)
-            K.gemm(ws["dqkv"], ws["ln1"][i], gw, a_mn=True, b_mn=True, accumulate=True)
+            fork()   # dqkv is final
+            wgrad(ws["dqkv"], ws["ln1"][i], gw)
             K.gemm(ws["dqkv"], wqkv, ws["d_ln"], b_mn=True)
             # LN1 + skip
             # next consumer of dx16: fc2 of layer i-1 (site 2i); for i == 0 the embedding dropout is applied below
+            join()
             K.layernorm_bwd(ws["d_ln"], ws["x_in"][i], self.w32(p + "layernorm_before.weight"), st[0], st[1], dx,
                             dx_other, ws["dx16"], self.g32(p + "layernorm_before.weight"),
                             self.g32(p + "layernorm_before.bias"),
