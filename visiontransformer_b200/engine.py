@@ -88,7 +88,7 @@ class Engine:
         self.rng_step = None         # device uint32 counter: advances once per dropout-enabled forward (graph-safe)
         self._drop = (0.0, 0.0)      # (hidden p, attention p) used by the last training forward
         self.launches = 0            # kernel launches issued by the last forward/backward (for bench bookkeeping)
-        self._two_streams = os.environ.get("VS_BWD_STREAMS", "2") != "1"
+        self._two_streams = os.environ.get("VS_BWD_STREAMS", "1") == "2"   # opt-in: measured neutral (11.03-11.10 vs 11.05 ms/step, r02)
         self._side = None
 
     # ------------------------------------------------------------------------------------------ parameters
@@ -444,8 +444,8 @@ class Engine:
         # Weight-gradient GEMMs run on a second stream, concurrently with the data-gradient chain: dW = dY^T X and
         # dX = dY W are independent, and at batch 64 every GEMM ends in a partly filled wave (12608 rows = 49.25 tiles
         # of 256) — the other kernel's CTAs fill the SMs that a kernel's tail wave leaves idle.  Forks / joins are
-        # events, so the pattern is captured into the step's CUDA graph as parallel branches.  VS_BWD_STREAMS=1 keeps
-        # everything on one stream.
+        # events, so the pattern is captured into the step's CUDA graph as parallel branches (VS_BWD_STREAMS=2).  VS_BWD_STREAMS=1 keeps
+        # everything on one stream (the default: the two-stream form measured neutral on one GPU, r02).
         side = self._side_stream() if self._two_streams else None
         cur = torch.cuda.current_stream()
 
