@@ -74,6 +74,17 @@ extern "C" int vs_multimem_allreduce_f32(void* multicast_ptr, int64_t n, int32_t
   const long long lo = (long long)rank * per;
   const long long hi = lo + per < n4 ? lo + per : n4;
   if (hi <= lo) return 0;
+  // The kernel uses no shared memory, but it must run with the SAME L1 / shared-memory split as the tcgen05 kernels
+  // (maximum shared memory): an SM that hosts only this kernel would otherwise be configured for a large L1, and a GEMM
+  // CTA arriving later has to wait for the SM to drain before the split can change (r02 timeline at 2 GPUs: GEMMs that
+  // STARTED while the reduction was resident finished exactly when it ended, 67 -> 94 us; GEMMs already running when it
+  // arrived were unaffected).
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(multimem_allreduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
   float* base = reinterpret_cast<float*>(multicast_ptr) + 4 * lo;
   VS_CHECK_CUDA(launch_k(multimem_allreduce_kernel, dim3((unsigned)nsm), dim3(128), (size_t)0, (cudaStream_t)stream, base,
                          hi - lo, scale));
