@@ -14,6 +14,8 @@
 // the NVLink traffic is 2/world of the bucket; the SMs only move addresses and 16-byte registers.
 // Cross-GPU ordering (all ranks finished producing the bucket / all ranks finished writing it back) is the caller's
 // job: visiontransformer_b200/dp.py brackets the launch with symmetric-memory barriers on its communication stream.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/vitseg.h"
 
@@ -74,19 +76,24 @@ extern "C" int vs_multimem_allreduce_f32(void* multicast_ptr, int64_t n, int32_t
   const long long lo = (long long)rank * per;
   const long long hi = lo + per < n4 ? lo + per : n4;
   if (hi <= lo) return 0;
-  // The kernel uses no shared memory, but it must run with the SAME L1 / shared-memory split as the tcgen05 kernels
-  // (maximum shared memory): an SM that hosts only this kernel would otherwise be configured for a large L1, and a GEMM
-  // CTA arriving later has to wait for the SM to drain before the split can change (r02 timeline at 2 GPUs: GEMMs that
-  // STARTED while the reduction was resident finished exactly when it ended, 67 -> 94 us; GEMMs already running when it
-  // arrived were unaffected).
-  static bool carveout_set = false;
-  if (!carveout_set) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(multimem_allreduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       (int)cudaSharedmemCarveoutMaxShared));
-    carveout_set = true;
+  // Tuning knobs (read once): VS_MM_CTAS = CTAs of the reduction kernel (default: one per SM), VS_MM_CARVEOUT=1 requests
+  // the maximum shared-memory carve-out so that a tcgen05 GEMM CTA can JOIN an SM that hosts only this kernel (without
+  // it, such a GEMM CTA waits for the SM to drain).  Measured at 2 GPUs (r02): joining is not the better deal — the two
+  // kernels then contend for the memory system (GEMM 69 -> 113 us, reduction 79 -> 172 us) instead of the GEMM starting
+  // 26 us late — so the default leaves the carve-out alone.
+  static int n_ctas = 0, carve = -1;
+  if (carve < 0) {
+    const char* e = getenv("VS_MM_CARVEOUT");
+    carve = (e && e[0] == '1') ? 1 : 0;
+    const char* c = getenv("VS_MM_CTAS");
+    n_ctas = c ? atoi(c) : 0;
+    if (n_ctas <= 0 || n_ctas > nsm) n_ctas = nsm;
+    if (carve)
+      VS_CHECK_CUDA(cudaFuncSetAttribute(multimem_allreduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)cudaSharedmemCarveoutMaxShared));
   }
   float* base = reinterpret_cast<float*>(multicast_ptr) + 4 * lo;
-  VS_CHECK_CUDA(launch_k(multimem_allreduce_kernel, dim3((unsigned)nsm), dim3(128), (size_t)0, (cudaStream_t)stream, base,
+  VS_CHECK_CUDA(launch_k(multimem_allreduce_kernel, dim3((unsigned)n_ctas), dim3(128), (size_t)0, (cudaStream_t)stream, base,
                          hi - lo, scale));
   return 0;
 }
