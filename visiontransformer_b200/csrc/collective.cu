@@ -42,17 +42,20 @@ multimem_allreduce_kernel(float* __restrict__ mc, long long n4, float scale) {
   pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  // two independent vectors in flight per thread (the NVLink round trip is ~2-3 us: 148 CTAs x 128 threads x 2 x 16 B
-  // = 0.6 MB outstanding)
-  for (; i + stride < n4; i += 2 * stride) {
-    float4 a = multimem_ld_reduce_add(mc + 4 * i);
-    float4 b = multimem_ld_reduce_add(mc + 4 * (i + stride));
-    a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
-    b.x *= scale; b.y *= scale; b.z *= scale; b.w *= scale;
-    multimem_st(mc + 4 * i, a);
-    multimem_st(mc + 4 * (i + stride), b);
+  // four independent vectors in flight per thread: the NVLink round trip is ~3 us, so the kernel's lifetime — which is
+  // what delays GEMM CTAs that want to START on its SMs — is set by the bytes outstanding (148 CTAs x 128 threads x 4 x
+  // 16 B = 1.2 MB)
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = multimem_ld_reduce_add(mc + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u].x *= scale; v[u].y *= scale; v[u].z *= scale; v[u].w *= scale;
+      multimem_st(mc + 4 * (i + u * stride), v[u]);
+    }
   }
-  if (i < n4) {
+  for (; i < n4; i += stride) {
     float4 a = multimem_ld_reduce_add(mc + 4 * i);
     a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
     multimem_st(mc + 4 * i, a);
