@@ -33,6 +33,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f by the magic-number add, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, well below the bf16 resolution of the probabilities it
+// feeds), exponent re-attached by an integer add.  The streaming forward at N = 1025 is bound by the XU pipe
+// (sm__inst_executed_pipe_xu 83 % in r01: one MUFU.EX2 per score at head_dim 64); evaluating a fraction of the scores
+// here moves that fraction off the XU pipe (the FlashAttention-4 trick).  Valid for x >= -126 (clamped).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float magic = 12582912.0f;              // 1.5 * 2^23: the low mantissa bits of (x + magic) hold round(x)
+  const float t = x + magic;
+  const float f = x - (t - magic);              // in [-0.5, 0.5]
+  float p = fmaf(0.05517141f, f, 0.24261075f);   // minimax in relative error (Lawson iteration on a 20001-point grid)
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.9999281f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // write 32 consecutive bf16 (columns c32*32 .. +32 of row r) of a [128 x 128] bf16 tile stored as two
 // [128 rows x 128 B] 128B-swizzled halves
 __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c32, const float (&f)[32]) {
@@ -70,7 +86,8 @@ struct AttnFwdSmem {
 };
 constexpr int kFwdThreads = 288;
 
-template <int kMinBlocks>
+// kPoly: 0 = every exponential on the XU pipe; 2 = every 2nd score, 4 = every 4th score through ex2_poly
+template <int kMinBlocks, int kPoly>
 __global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
@@ -264,7 +281,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(fmaf(sc[i], sl2, -m_off)), p1 = ex2_approx(fmaf(sc[i + 1], sl2, -m_off));
+        const float p0 = ex2_approx(fmaf(sc[i], sl2, -m_off));
+        const float x1 = fmaf(sc[i + 1], sl2, -m_off);
+        const float p1 = (kPoly == 2 || (kPoly == 4 && (i & 2))) ? ex2_poly(x1) : ex2_approx(x1);
         l_blk += p0 + p1;   // row sum in dropout-scaled units (the normaliser uses the un-dropped probabilities)
         bool k0 = true, k1 = true;
         if (drop.thresh != 0u)   // keys 2k, 2k+1 of a query row share one hash
@@ -937,16 +956,24 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   }
   rc = make_tok_tmap(&tkv, qkv, B, N, 3 * H * kDH, kFKB);
   if (rc) return rc;
-  static bool attr_stream = false;
-  if (!attr_stream) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       AttnFwdSmem::kTotal));
-    attr_stream = true;
+  // VS_ATTN_POLY = 0 | 2 | 4: fraction of the exponentials evaluated on the FMA pipe (none, every 2nd, every 4th score)
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("VS_ATTN_POLY");
+    poly = e ? atoi(e) : 4;
+    if (poly != 0 && poly != 2 && poly != 4) poly = 4;
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
   }
   DropCfg dc;
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
   dim3 grid((N + kBQ - 1) / kBQ, H, B);
-  launch_k(attn_fwd_kernel<2>, dim3(grid), dim3(kFwdThreads), (size_t)(AttnFwdSmem::kTotal), (cudaStream_t)stream, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dc);
+  const size_t smem = (size_t)AttnFwdSmem::kTotal;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (poly == 0) launch_k(attn_fwd_kernel<2, 0>, grid, dim3(kFwdThreads), smem, st, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dc);
+  else if (poly == 2) launch_k(attn_fwd_kernel<2, 2>, grid, dim3(kFwdThreads), smem, st, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dc);
+  else launch_k(attn_fwd_kernel<2, 4>, grid, dim3(kFwdThreads), smem, st, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dc);
   VS_CHECK_LAUNCH();
   return 0;
 }
