@@ -956,12 +956,16 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
   }
   rc = make_tok_tmap(&tkv, qkv, B, N, 3 * H * kDH, kFKB);
   if (rc) return rc;
-  // VS_ATTN_POLY = 0 | 2 | 4: fraction of the exponentials evaluated on the FMA pipe (none, every 2nd, every 4th score)
+  // VS_ATTN_POLY = 0 | 2 | 4: fraction of the exponentials evaluated on the FMA pipe (none, every 2nd, every 4th score).
+  // r02 measurement (B = 32, H = 12, N = 1025): 338.8 us without, 388.8 us with every 4th, 381.2 us with every 2nd score
+  // on the FMA pipe: the XU pipe is busy (83 %) but the issue slots are the tighter resource once 7 instructions replace
+  // one MUFU; and the forward probabilities then differ from the ones the backward recomputes with ex2.approx (gradient
+  // error of the 16-layer patch-8 model 6 % -> 10 %).  Kept for the record, off by default.
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("VS_ATTN_POLY");
-    poly = e ? atoi(e) : 4;
-    if (poly != 0 && poly != 2 && poly != 4) poly = 4;
+    poly = e ? atoi(e) : 0;   // default off: measured SLOWER (338.8 -> 388.8 / 381.2 us at N = 1025) — see below
+    if (poly != 0 && poly != 2 && poly != 4) poly = 0;
     VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
     VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
     VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::kTotal));
