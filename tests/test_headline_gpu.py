@@ -216,3 +216,31 @@ def test_vitb16_200_step_loss_curve_and_trained_argmax(golden_dir, which):
           f"{agree_fp32_weights:.5f} with the fp32 master weights on the oracle side")
     assert agree >= (0.999 if which == "adam_lr1e-5" else 0.995)
     assert agree_fp32_weights >= 0.97
+
+
+@pytest.mark.parametrize("name,arch,inter,S", [
+    ("ViT-B/16 @512 (BASELINE configs[4])", dict(patch_size=16, hidden_size=768, num_hidden_layers=12, num_attention_heads=12), 3072, 512),
+    ("ViT-L/16 @384 (BASELINE configs[3])", dict(patch_size=16, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16), 4096, 384),
+])
+def test_other_baseline_configs_forward_vs_oracle(name, arch, inter, S):
+    """The models of BASELINE configs[3] and [4] at their real sizes (1025 / 577 tokens: streaming attention, 1024-wide
+    and 4096-deep MLP GEMMs), one image, eval forward against the fp32 oracle on this box's CPU: logits within 1e-2, fused
+    mask equal to the argmax of the logits."""
+    from visiontransformer_b200.ce.classes import LightningViTModel
+    dev = _dev()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cfg = O.OracleConfig(num_classes=17, image_size=S, intermediate_size=inter, **arch)
+    sd = O.seeded_state_dict(cfg, 77, head_gain=4.0)
+    m = LightningViTModel(17, arch["patch_size"], arch["hidden_size"], arch["num_hidden_layers"], arch["num_attention_heads"],
+                          image_size=S, intermediate_size=inter)
+    m.load_state_dict(O.to_module_state_dict(sd, "model."), strict=True)
+    m = m.to(dev).eval()
+    x = O.synthetic_images(1, S, seed=78)
+    with torch.no_grad():
+        full = m(x.to(dev)).cpu()
+        mask = m.model.predict_mask(x.to(dev)).cpu().long()
+        ref = O.forward(sd, x, cfg)
+    err = _relmax(full, ref)
+    print(f"{name}: logits err {err:.2e}")
+    assert err < LOGIT_TOL
+    assert (mask == full.argmax(1)).float().mean().item() > 0.9999
