@@ -656,7 +656,7 @@ def run_ours(args, cfg):
     tot_ms = sum(t for _, t in gemm_events)
     roof = None
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic_r02.json")
     if os.path.exists(tpath) and args.config == "ce":  # dram bytes per GEMM launch from one ncu pass over this step
         with open(tpath) as f:
             traffic = float(json.load(f)["traffic_bytes_per_launch"])
@@ -664,7 +664,7 @@ def run_ours(args, cfg):
         ach = tot_flops / (tot_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_sus, "unit": "TFLOP/s", "frac": ach / peak_sus,
                 "peak_burst": peak_burst, "frac_burst": ach / peak_burst,
-                "traffic": traffic, "traffic_unit": "bytes per launch (mean over the GEMM launches of one step; profiles/gemm_traffic_r01.json)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (mean over the GEMM launches of one step; profiles/gemm_traffic_r02.json)",
                 "kernel": "vs::gemm_kernel (tcgen05, all variants)", "launches_timed": len(gemm_events),
                 "timing": f"CUDA events around each GEMM launch in {n_eager} eager (non-graph) steps of the same workload",
                 "share_of_step": (tot_ms / n_eager) / (ms / args.steps),
