@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 2
+#define VS_ABI_VERSION 3
 
 const char* vs_last_error(void);
 int vs_abi_version(void);
@@ -51,6 +51,7 @@ int vs_device_sm_count(void);
  *   v *= gelu'(aux[m,n])  | v = aux[m,n]>0?v:0 (aux_mode 1 | 2; aux bf16 [M, ldaux])
  *   v += residual[rm, n]                       (residual != NULL; fp32, ld ldr)
  *   store to out (out_dtype 0 = bf16, 1 = fp32); accumulate != 0: atomic fp32 add (split-K / grad accumulation)
+ *   out_colsum[n] += sum_m bf16(out[m,n])       (out_colsum != NULL; bf16 outputs)
  * Broadcast residual (patch embedding + position embedding, TF:117-124): row_tokens = T1 > 0 reads residual row
  *   (m % T1), i.e. a [T1, N] table shared by every image; 0 = residual row m.
  * split_k: 0 = automatic (only >1 when accumulate != 0), else the number of K partitions.
@@ -85,6 +86,11 @@ typedef struct vs_gemm_desc {
   float dropout_p;
   const uint32_t* dropout_seed;
   uint32_t dropout_site;
+  /* ABI 3: column sums of the (bf16-rounded) output, out_colsum[n] += sum_m out[m,n] — the bias gradient of the Linear
+   * that produced this GEMM's A gradient (autograd of nn.Linear bias, TF:290).  bf16 outputs only.  Formed inside the
+   * epilogue from the staged shared-memory tile when the TMA-store epilogue runs, by a following vs_colsum_bf16 launch
+   * otherwise: the result is the same either way. */
+  float* out_colsum;
 } vs_gemm_desc;
 
 int vs_gemm_bf16(const vs_gemm_desc* d, void* stream);

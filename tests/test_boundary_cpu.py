@@ -117,7 +117,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/vitseg.h but not exported"
     assert set(_lib.EXPORTED_SYMBOLS) == set(syms)
     lib.vs_abi_version.restype = ctypes.c_int
-    assert lib.vs_abi_version() == 2
+    assert lib.vs_abi_version() == 3
 
 
 def test_compute_entry_fails_without_device():

@@ -56,13 +56,16 @@ def test_gemm_epilogue_dropout_and_layernorm_bwd_mask():
     a = torch.randn(M, Kd, device=dev).bfloat16()
     w = (torch.randn(N, Kd, device=dev) * 0.1).bfloat16()
     bias, res = torch.randn(N, device=dev), torch.randn(M, N, device=dev)
-    out = torch.empty(M, N, device=dev)
-    K.gemm(a, w, out, bias=bias, residual=res, dropout=drop)
     mask = _mask(K, M * N, 0, drop).view(M, N)
     thresh = round(p * 65536)
     scale = 1.0 / (1.0 - thresh / 65536.0)
     ref = (a.float() @ w.float().t() + bias) * mask * scale + res
-    assert _rel(out, ref) < 1e-5
+    # every tile configuration: 1, 2, 4 use the smem-transposed fp32 epilogue, 3 and 5 (128-column tiles) the TMA
+    # residual-prefetch epilogue — the element -> mask map must be the same in all of them
+    for cfg in (0, 1, 2, 3, 4, 5):
+        out = torch.empty(M, N, device=dev)
+        K.gemm(a, w, out, bias=bias, residual=res, dropout=drop, tile_cfg=cfg)
+        assert _rel(out, ref) < 1e-5, cfg
     # LayerNorm backward: fp32 dx unmasked, bf16 copy masked with the same site
     D = N
     x = torch.randn(M, D, device=dev)

@@ -130,6 +130,20 @@ def probe_gemm():
         case(300, 48, 128, False, True, cfg=cfg)
         case(40000, 512, 64, False, False, bias=True, act=1, out2=True, cfg=cfg)
 
+    def colsum_case():
+        # out_colsum: fused into the TMA-store epilogue (cfg 1, 3, 4, 5), a pass after the GEMM otherwise (cfg 2)
+        for cfg in (0, 1, 2, 3, 4, 5):
+            M, N, Kd = 5000, 1024, 256
+            a = bf(torch.randn(M, Kd, device=dev))
+            b = bf(torch.randn(N, Kd, device=dev) * 0.5)
+            aux = bf(torch.randn(M, N, device=dev))
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            cs = torch.randn(N, device=dev)
+            cs0 = cs.clone()
+            K.gemm(a, b.t().contiguous(), out, b_mn=True, aux=aux, aux_mode=1, colsum=cs, tile_cfg=cfg)
+            report(f"gemm fused column sums cfg{cfg}", rel(cs, cs0 + out.float().sum(0)), 2e-5)
+    run("gemm colsum", colsum_case)
+
     def strided_case():
         # bf16 output / aux that are column slices of wider matrices (row stride != N), as the engine's views can be
         M, N, Kd = 777, 256, 192

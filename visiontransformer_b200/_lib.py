@@ -29,6 +29,7 @@ class GemmDesc(C.Structure):
         ("residual", c_void_p), ("ldr", c_i64),
         ("row_tokens", c_int), ("split_k", c_int), ("tile_cfg", c_int),
         ("dropout_p", c_float), ("dropout_seed", c_void_p), ("dropout_site", C.c_uint32),
+        ("out_colsum", c_void_p),
     ]
 
 

@@ -475,12 +475,12 @@ class Engine:
             # LayerNorm backward that produced dx16)
             fork()
             wgrad(ws["dx16"], ws["h_act"][i], self.g32(p + "output.dense.weight"))
+            # (the fc1 bias gradient = column sums of dh comes out of this GEMM's epilogue)
             K.gemm(ws["dx16"], self.w16(p + "output.dense.weight"), ws["dh"], b_mn=True, aux=ws["h_pre"][i],
-                   aux_mode=K.AUX_GELU_GRAD)
+                   aux_mode=K.AUX_GELU_GRAD, colsum=self.g32(p + "intermediate.dense.bias"))
             # fc1
             fork()   # dh is final
             wgrad(ws["dh"], ws["ln2"][i], self.g32(p + "intermediate.dense.weight"))
-            K.colsum(ws["dh"], self.g32(p + "intermediate.dense.bias"), accumulate=True)
             K.gemm(ws["dh"], self.w16(p + "intermediate.dense.weight"), ws["d_ln"], b_mn=True)
             # LN2 + skip (overwrites dx16, which the fc2 weight gradient reads: join first)
             join()
@@ -513,7 +513,7 @@ class Engine:
                             dropout=self._site(p_hid, 2 * i) if i > 0 else None,
                             dbias=self.g32(f"backbone.encoder.layer.{i - 1}.output.dense.bias") if i > 0 else None)
             dx, dx_other = dx_other, dx
-            n += 16
+            n += 15
             if hook:
                 hook(f"layer{i}")
         # --- embeddings

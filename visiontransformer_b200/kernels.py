@@ -72,8 +72,12 @@ _TUNED = {}
 def _autotune(d, out, accumulate):
     lib = _lib.load()
     st = stream()
-    saved_out = d.out
+    saved_out, saved_colsum = d.out, d.out_colsum
     scratch = None
+    cs_scratch = None
+    if d.out_colsum:   # trial launches must not add into the caller's bias-gradient buffer either
+        cs_scratch = torch.zeros(d.N, device=out.device, dtype=F32)
+        d.out_colsum = ptr(cs_scratch)
     if accumulate:   # trial launches must not add into the caller's gradient buffer
         scratch = torch.empty_like(out)
         d.out, d.ldo = ptr(scratch), scratch.stride(0)
@@ -97,6 +101,7 @@ def _autotune(d, out, accumulate):
                 best, best_ms = cfg, ms
     finally:
         d.out = saved_out
+        d.out_colsum = saved_colsum
         if accumulate:
             d.ldo = out.stride(0)
         d.tile_cfg = 0
@@ -110,7 +115,7 @@ def tuned_configs():
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=None, aux=None, aux_mode=AUX_NONE,
          residual=None, row_tokens=0, accumulate=False, split_k=0, tile_cfg=0, M=None, N=None, K=None,
-         dropout=None):
+         dropout=None, colsum=None):
     """out[M,N] = epilogue(sum_k A(m,k) B(n,k)); see include/vitseg.h:vs_gemm_desc.
 
     a: bf16 [M,K] (or [K,M] when a_mn); b: bf16 [N,K] (or [K,N] when b_mn); out: bf16 or fp32 2-D view."""
@@ -145,6 +150,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=Non
     if residual is not None:
         assert residual.dtype == F32
         d.residual, d.ldr = ptr(residual), _rowmajor(residual, "residual")
+    if colsum is not None:   # out_colsum[n] += sum_m out[m, n] (bias gradient of the producing Linear), bf16 outputs
+        assert colsum.dtype == F32 and colsum.is_contiguous() and colsum.numel() == N and out.dtype == BF16
+        d.out_colsum = ptr(colsum)
     d.row_tokens = row_tokens
     d.split_k = split_k
     d.tile_cfg = tile_cfg
@@ -152,7 +160,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=ACT_NONE, out2=Non
         d.dropout_p, d.dropout_seed, d.dropout_site = dropout[0], ptr(dropout[1]), dropout[2]
     if tile_cfg == 0 and _AUTOTUNE:
         key = (M, N, K, bool(a_mn), bool(b_mn), d.out_dtype, bool(accumulate), bias is not None, act, out2 is not None,
-               aux_mode, residual is not None, row_tokens > 0, d.dropout_p > 0.0, split_k)
+               aux_mode, residual is not None, row_tokens > 0, d.dropout_p > 0.0, split_k, colsum is not None)
         cfg = _TUNED.get(key)
         if cfg is None and not torch.cuda.is_current_stream_capturing():
             cfg = _TUNED[key] = _autotune(d, out, accumulate)
