@@ -512,33 +512,41 @@ __device__ __forceinline__ void epilogue_tile_bf16_tma(const GemmParams& p, cons
     }
     fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
     __syncwarp();
+    if (lane == 0 && row0 < p.M && col0 < p.N) {
+      tma_store_2d(final_pass ? tm_out : tm_out2, stg, col0, row0);
+      bulk_commit();
+    }
     if (final_pass && p.colsum != nullptr && col0 < p.N) {
       // bias gradient of the producing Linear: column sums of this warp's [32 x W] tile, read back from the staged
       // shared-memory copy (i.e. of the bf16-rounded values, exactly what a separate pass over the output would
       // sum).  Lane l owns the 32-bit word l of every 128-byte row (2 columns) — 32 conflict-free LDS (the swizzle
       // permutes 16-byte units inside a row, a row still covers all banks); rows past M hold padding and are skipped.
-      // One coalesced red per warp and tile: replaces a 77 MB re-read of the fc1 hidden gradient per layer (r01 / r02
-      // step tables: 12 colsum launches, 19 us each).
+      // The TMA store of the tile has already been issued (both only read it).  One coalesced red per warp and tile;
+      // replaces a 77 MB re-read of the fc1 hidden gradient per layer (r01 / r02 step tables: 12 colsum launches of 19 us).
       const int nrows = min(32, p.M - row0);
       constexpr int kWords = W / 2;            // 32-bit words per row
       if (lane < kWords) {
-        float s0 = 0.0f, s1 = 0.0f;
-        for (int rr = 0; rr < nrows; ++rr) {
-          const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + stg_off<W>(rr, lane >> 2) + ((lane & 3) << 2));
-          const float2 f2 = unpack_bf16(wv);
-          s0 += f2.x;
-          s1 += f2.y;
+        float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sb[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // 4 independent chains per column
+#pragma unroll
+        for (int r4 = 0; r4 < 32; r4 += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = r4 + u;
+            if (rr < nrows) {
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + stg_off<W>(rr, lane >> 2) + ((lane & 3) << 2));
+              const float2 f2 = unpack_bf16(wv);
+              sa[u] += f2.x;
+              sb[u] += f2.y;
+            }
+          }
         }
+        const float s0 = (sa[0] + sa[1]) + (sa[2] + sa[3]), s1 = (sb[0] + sb[1]) + (sb[2] + sb[3]);
         const int n = col0 + 2 * lane;
         if (n < p.N) {
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n), "f"(s0) : "memory");
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n + 1), "f"(s1) : "memory");
         }
       }
-    }
-    if (lane == 0 && row0 < p.M && col0 < p.N) {
-      tma_store_2d(final_pass ? tm_out : tm_out2, stg, col0, row0);
-      bulk_commit();
     }
   }
 }
@@ -1067,7 +1075,13 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   const bool f32_tma = epi_env == 1 && d->out_dtype == 1 && !d->accumulate && d->row_tokens == 0 && tc.bn == 128 &&
                        d->aux_mode == 0 && d->out2 == nullptr && d->ldo % 4 == 0 && (d->residual == nullptr || d->ldr % 4 == 0);
   const int epi = (want_tma && tc.bn != 192) ? 1 : (f32_tma ? 2 : 0);
-  p.colsum = epi == 1 ? d->out_colsum : nullptr;   // fused into the staged-tile epilogue; otherwise a pass after the GEMM
+  // fused into the staged-tile epilogue; otherwise (or with VS_GEMM_COLSUM=separate, for A/B runs) a pass after the GEMM
+  static int colsum_fused = -1;
+  if (colsum_fused < 0) {
+    const char* e = getenv("VS_GEMM_COLSUM");
+    colsum_fused = (e && strcmp(e, "separate") == 0) ? 0 : 1;
+  }
+  p.colsum = (epi == 1 && colsum_fused) ? d->out_colsum : nullptr;
   int splits = tc.splits;
   if (splits > p.kblocks) splits = p.kblocks;
   // every split must own at least one k-block
