@@ -142,6 +142,18 @@ def probe_gemm():
             cs0 = cs.clone()
             K.gemm(a, b.t().contiguous(), out, b_mn=True, aux=aux, aux_mode=1, colsum=cs, tile_cfg=cfg)
             report(f"gemm fused column sums cfg{cfg}", rel(cs, cs0 + out.float().sum(0)), 2e-5)
+            x = aux.float().requires_grad_(True)
+            (gg,) = torch.autograd.grad(F.gelu(x).sum(), x)
+            report(f"   output (column-persistent tile order) cfg{cfg}", rel(out, (a.float() @ b.float().t()) * gg), 1e-2)
+        # ragged shapes: 13 row tiles on 6 units per column tile, a 16-column tail, fewer row tiles than units per column
+        for (M, N, Kd) in ((3200, 3072, 128), (300, 48, 128), (12608, 3072, 768)):
+            a = bf(torch.randn(M, Kd, device=dev))
+            b = bf(torch.randn(N, Kd, device=dev) * 0.5)
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            cs = torch.zeros(N, device=dev)
+            K.gemm(a, b, out, colsum=cs)
+            report(f"gemm fused column sums {M}x{N}x{Kd}", rel(cs, out.float().sum(0)), 2e-5)
+            report(f"   output {M}x{N}x{Kd}", rel(out, a.float() @ b.float().t()), 1e-2)
     run("gemm colsum", colsum_case)
 
     def strided_case():

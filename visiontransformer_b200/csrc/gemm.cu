@@ -50,6 +50,8 @@ struct GemmParams {
   DropCfg drop;  // hidden-state dropout applied to (acc + bias) before the residual add (fp32 outputs only)
   int dynamic;   // 1: tiles are handed out by cluster launch control (grid = one cluster per work item)
   float* colsum; // EPI 1: out_colsum[n] += sum over rows of the bf16-rounded output (bias gradient), or nullptr
+  int raster;    // 1: column-persistent tile order (see decode_work): a unit keeps ONE column tile for all its tiles
+  int per;       //    units per column tile in that order
 };
 
 // EPI = 0: register-direct / smem-transposed epilogues (fp32 outputs, accumulation, BN = 192).
@@ -186,6 +188,29 @@ __device__ __forceinline__ int clc_decode(const uint4* resp) {
       : "memory");
   return valid ? (int)x : -1;
 }
+// work item -> (k split, row tile, column tile).
+//   default order : w = split * tiles + tm * tiles_n + tn, handed out round-robin (unit u takes w = u, u + U, ...): the
+//                   units of one "wave" share A row tiles and sweep the column tiles.
+//   raster = 1    : column-persistent order for GEMMs that also form the column sums of their output: unit u keeps the
+//                   column tile tn = u % tiles_n for ALL of its tiles (row tiles j, j + per, ... with j = u / tiles_n), so
+//                   an epilogue warp owns the same columns throughout and accumulates their sums in registers — one
+//                   reduction per warp and kernel instead of one per warp and tile (per * 8 same-address reductions per
+//                   column instead of tiles_m * 8).  The grid is per * tiles_n units; splits = 1.
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int tiles, int nunits, int& split, int& tm,
+                                            int& tn) {
+  if (p.raster) {
+    const int u = w % nunits, i = w / nunits;
+    split = 0;
+    tn = u % p.tiles_n;
+    tm = u / p.tiles_n + i * p.per;
+  } else {
+    split = w / tiles;
+    const int t = w - split * tiles;
+    tm = t / p.tiles_n;
+    tn = t - tm * p.tiles_n;
+  }
+}
+
 // iteration state of one consumer warp over the work items of its cluster
 template <int CTA2>
 struct TileIter {
@@ -193,8 +218,13 @@ struct TileIter {
   int it, step, total;
   uint32_t rank;
   bool dynamic;
+  int raster_per, tiles_m, tiles_n;   // raster_per > 0: column-persistent order (decode_work)
   __device__ __forceinline__ int next(int w, int lane) {
-    if (!dynamic) return (w + step < total) ? w + step : -1;
+    if (!dynamic) {
+      const int wn = w + step;
+      if (raster_per > 0) return ((wn % step) / tiles_n + (wn / step) * raster_per < tiles_m) ? wn : -1;
+      return (wn < total) ? wn : -1;
+    }
     const int slot = it & (kSched - 1);
     mbar_wait(&ss->full[slot], (uint32_t)(it / kSched) & 1u);
     const int x = clc_decode(&ss->resp[slot]);
@@ -431,7 +461,7 @@ __device__ __forceinline__ void epilogue_tile_bf16_tma(const GemmParams& p, cons
                                                        const CUtensorMap* tm_out2, uint8_t* stg, uint64_t* aux_bar,
                                                        uint32_t aux_phase, uint32_t tmem_addr, uint64_t* tfull,
                                                        uint32_t tfull_phase, int row0, int col0, bool first_split,
-                                                       int lane) {
+                                                       int lane, float& cs0, float& cs1) {
   constexpr int W = kChunks * 16;
   const bool add_bias = p.bias != nullptr && first_split;
   const int npass = p.out2 != nullptr ? 2 : 1;
@@ -541,10 +571,15 @@ __device__ __forceinline__ void epilogue_tile_bf16_tma(const GemmParams& p, cons
           }
         }
         const float s0 = (sa[0] + sa[1]) + (sa[2] + sa[3]), s1 = (sb[0] + sb[1]) + (sb[2] + sb[3]);
-        const int n = col0 + 2 * lane;
-        if (n < p.N) {
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n), "f"(s0) : "memory");
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n + 1), "f"(s1) : "memory");
+        if (p.raster) {   // same columns for every tile of this warp: keep the sums, one reduction at the end of the kernel
+          cs0 += s0;
+          cs1 += s1;
+        } else {
+          const int n = col0 + 2 * lane;
+          if (n < p.N) {
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n), "f"(s0) : "memory");
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n + 1), "f"(s1) : "memory");
+          }
         }
       }
     }
@@ -716,7 +751,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
   const int unit = blockIdx.x / kNCta;
   const int nunits = gridDim.x / kNCta;
-  TileIter<CTA2> ti{ss, 0, nunits, total_work, rank, p.dynamic != 0};
+  TileIter<CTA2> ti{ss, 0, nunits, total_work, rank, p.dynamic != 0, p.raster ? p.per : 0, p.tiles_m, p.tiles_n};
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (each CTA loads its A rows and its B half)
@@ -725,9 +760,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     for (int w = unit; w >= 0; w = ti.next(w, lane)) {
-      const int split = w / tiles;
-      const int t = w - split * tiles;
-      const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      int split, tm, tn;
+      decode_work(p, w, tiles, nunits, split, tm, tn);
       const int m0 = tm * (BM * kNCta) + rank * BM;
       const int n0 = tn * BN + rank * L::kBNH;
       const int kb0 = split * kb_per_split;
@@ -774,7 +808,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = unit; w >= 0; w = ti.next(w, lane)) {
-        const int split = w / tiles;
+        int split, tm_unused, tn_unused;
+        decode_work(p, w, tiles, nunits, split, tm_unused, tn_unused);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -846,8 +881,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t acc_phase = 0;
     uint32_t aux_phase = 0;
     auto tile_origin = [&](int w, int& row0, int& col0) {
-      const int t = w % tiles;
-      const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      int split_unused, tm, tn;
+      decode_work(p, w, tiles, nunits, split_unused, tm, tn);
       row0 = tm * (BM * kNCta) + rank * BM + quad * 32;
       col0 = tn * BN + slice * kColsPerWarp;
     };
@@ -868,10 +903,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (res_tma && lane == 0) load_res(unit, 0);
     int w_next = ti.next(unit, lane);   // one work item ahead: the aux / residual tile of the next item is prefetched
     int ntile = 0;
+    float cs0 = 0.0f, cs1 = 0.0f;   // raster = 1: this lane's two column sums, carried across the warp's tiles
+    int cs_col0 = -1;
     for (int w = unit; w >= 0; w = w_next, w_next = (w >= 0 ? ti.next(w, lane) : -1), ++ntile) {
-      const int split = w / tiles;
+      const int split = p.raster ? 0 : w / tiles;
       int row0, col0;
       tile_origin(w, row0, col0);
+      cs_col0 = col0;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + slice * kColsPerWarp);
       if constexpr (EPI == 2) {
         const int b = ntile & 1;
@@ -883,7 +921,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                        &tfull_bar[acc], acc_phase, row0, col0, lane);
       } else if constexpr (EPI == 1) {
         epilogue_tile_bf16_tma<kChunks>(p, &tmap_out, &tmap_out2, stg, &aux_bar[ew], aux_phase, taddr, &tfull_bar[acc],
-                                        acc_phase, row0, col0, split == 0, lane);
+                                        acc_phase, row0, col0, split == 0, lane, cs0, cs1);
       } else if (p.out_f32) {
         epilogue_tile_f32<kChunks>(p, stg, taddr, &tfull_bar[acc], acc_phase, row0, col0, split == 0, lane);
       } else {
@@ -903,6 +941,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (EPI == 1 && p.colsum != nullptr && p.raster && cs_col0 >= 0 && lane < kColsPerWarp / 2) {
+      const int n = cs_col0 + 2 * lane;
+      if (n < p.N) {
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n), "f"(cs0) : "memory");
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.colsum + n + 1), "f"(cs1) : "memory");
+      }
     }
     if (EPI && lane == 0) bulk_wait_read0();   // shared memory must outlive the last store's read
   }
@@ -1165,15 +1210,35 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
     sched_env = (e && strcmp(e, "clc") == 0) ? 1 : 0;
   }
   p.dynamic = sched_env;
+  // column-persistent tile order when the kernel also sums the columns of its output (decode_work): needs at least one
+  // unit per column tile and a single k split; VS_GEMM_RASTER=0 keeps the default order (one reduction per warp and tile)
+  p.raster = 0;
+  p.per = 0;
+  int units_eff = 0;
+  {
+    static int raster_env = -1;
+    if (raster_env < 0) {
+      const char* e = getenv("VS_GEMM_RASTER");
+      raster_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int units = tc.cta2 ? nsm / 2 : nsm;
+    if (p.colsum != nullptr && raster_env && !p.dynamic && splits == 1 && p.tiles_n <= units) {
+      int per = units / p.tiles_n;
+      if (per > p.tiles_m) per = p.tiles_m;
+      p.raster = 1;
+      p.per = per;
+      units_eff = per * p.tiles_n;
+    }
+  }
   int rc = 0;
   if (tc.cta2) {
     const int pairs = nsm / 2;
-    const int grid = p.dynamic ? 2 * total : 2 * (total < pairs ? total : pairs);
+    const int grid = p.raster ? 2 * units_eff : (p.dynamic ? 2 * total : 2 * (total < pairs ? total : pairs));
     if (BN == 256) rc = launch_epi<256, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     else if (BN == 192) rc = launch_major<192, 1, 0>(d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     else rc = launch_epi<128, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
   } else {
-    const int grid = p.dynamic ? total : (total < nsm ? total : nsm);
+    const int grid = p.raster ? units_eff : (p.dynamic ? total : (total < nsm ? total : nsm));
     if (BN == 256) rc = launch_epi<256, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     else rc = launch_epi<128, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
   }
