@@ -90,6 +90,7 @@ class Engine:
         self.launches = 0            # kernel launches issued by the last forward/backward (for bench bookkeeping)
         self._two_streams = os.environ.get("VS_BWD_STREAMS", "1") == "2"   # opt-in: measured neutral (11.03-11.10 vs 11.05 ms/step, r02)
         self._side = None
+        self._fuse_colsum = os.environ.get("VS_FUSE_COLSUM", "0") == "1"
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -475,12 +476,17 @@ class Engine:
             # LayerNorm backward that produced dx16)
             fork()
             wgrad(ws["dx16"], ws["h_act"][i], self.g32(p + "output.dense.weight"))
-            # (the fc1 bias gradient = column sums of dh comes out of this GEMM's epilogue)
+            # VS_FUSE_COLSUM=1: the fc1 bias gradient (column sums of dh) comes out of this GEMM's epilogue (out_colsum,
+            # column-persistent tile order); default: a separate column-sum pass.  Measured -0.1 ms per step for the fused
+            # form, inside the box-to-box variation, while the GEMM kernel then carries non-GEMM work (r02 A/B logs)
             K.gemm(ws["dx16"], self.w16(p + "output.dense.weight"), ws["dh"], b_mn=True, aux=ws["h_pre"][i],
-                   aux_mode=K.AUX_GELU_GRAD, colsum=self.g32(p + "intermediate.dense.bias"))
+                   aux_mode=K.AUX_GELU_GRAD,
+                   colsum=self.g32(p + "intermediate.dense.bias") if self._fuse_colsum else None)
             # fc1
             fork()   # dh is final
             wgrad(ws["dh"], ws["ln2"][i], self.g32(p + "intermediate.dense.weight"))
+            if not self._fuse_colsum:
+                K.colsum(ws["dh"], self.g32(p + "intermediate.dense.bias"), accumulate=True)
             K.gemm(ws["dh"], self.w16(p + "intermediate.dense.weight"), ws["d_ln"], b_mn=True)
             # LN2 + skip (overwrites dx16, which the fc2 weight gradient reads: join first)
             join()
@@ -513,7 +519,7 @@ class Engine:
                             dropout=self._site(p_hid, 2 * i) if i > 0 else None,
                             dbias=self.g32(f"backbone.encoder.layer.{i - 1}.output.dense.bias") if i > 0 else None)
             dx, dx_other = dx_other, dx
-            n += 15
+            n += 15 if self._fuse_colsum else 16
             if hook:
                 hook(f"layer{i}")
         # --- embeddings
