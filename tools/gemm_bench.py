@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 CFG = {0: "auto", 1: "pair256", 2: "pair192", 3: "pair128", 4: "single256", 5: "single128"}
 
 
-def bench(M, N, Kd, a_mn=False, b_mn=False, cfgs=(0, 1, 2, 4), reps=20, **kw):
+def bench(M, N, Kd, a_mn=False, b_mn=False, cfgs=(0, 1, 2, 3), reps=20, **kw):
     a = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).to(torch.bfloat16)
     b = torch.randn((Kd, N) if b_mn else (N, Kd), device=dev).to(torch.bfloat16)
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if kw.get("f32") else torch.bfloat16)
@@ -36,10 +36,16 @@ def bench(M, N, Kd, a_mn=False, b_mn=False, cfgs=(0, 1, 2, 4), reps=20, **kw):
 
 
 if __name__ == "__main__":
-    # pure main loop: one wave exactly, long K
-    bench(18944, 256, 16384, cfgs=(1, 4))
-    bench(18944, 512, 8192, cfgs=(1, 4))
-    bench(8192, 8192, 8192, cfgs=(1, 2, 4))
+    if "model" not in sys.argv[1:]:
+        # pure main loop: one wave exactly, long K
+        bench(18944, 256, 16384, cfgs=(1, 4))
+        bench(18944, 512, 8192, cfgs=(1, 4))
+        bench(8192, 8192, 8192, cfgs=(1, 2, 4))
+    else:
+        # the data-gradient GEMMs of the ViT-B/16 step (MN-major weights), all pair configurations
+        bench(12608, 768, 768, b_mn=True, cfgs=(0, 1, 2, 3))
+        bench(12608, 768, 2304, b_mn=True, cfgs=(0, 1, 2, 3))
+        bench(12608, 3072, 768, b_mn=True, cfgs=(0, 1, 2, 3))
     # model shapes
     bench(12608, 2304, 768, bias=True)
     bench(12608, 768, 768, bias=True, res=True, f32=True)

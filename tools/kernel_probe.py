@@ -130,6 +130,16 @@ def probe_gemm():
         case(300, 48, 128, False, True, cfg=cfg)
         case(40000, 512, 64, False, False, bias=True, act=1, out2=True, cfg=cfg)
 
+    # partial last wave cut into column sub-tiles (VS_GEMM_TAIL): the headline data-gradient / forward shapes, whose tile
+    # counts leave 2 - 8 tiles for the last wave, in every tile configuration
+    for cfg in (1, 2, 3, 4, 5):
+        case(12608, 768, 3072, False, True, cfg=cfg)
+        case(12608, 768, 768, False, True, cfg=cfg)
+        case(12608, 2304, 768, False, False, bias=True, cfg=cfg)
+        case(12608, 3072, 768, False, True, aux_mode=1, cfg=cfg)
+        case(12608, 3072, 768, False, False, bias=True, act=1, out2=True, cfg=cfg)
+        case(12608, 768, 3072, False, False, bias=True, res=True, f32=True, cfg=cfg)
+
     def colsum_case():
         # out_colsum: fused into the TMA-store epilogue (cfg 1, 3, 4, 5), a pass after the GEMM otherwise (cfg 2)
         for cfg in (0, 1, 2, 3, 4, 5):

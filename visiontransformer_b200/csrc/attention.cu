@@ -803,13 +803,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
         const bool q_ok = q < N;
         const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
         const float lse2 = lse_n * kLog2e, dlt = dlt_n;
+        // all 32 query rows of this warp lie beyond the sequence (N = 197: the last quadrant of the second tile):
+        // P = dS = 0 without reading S / dP, and no dQ rows to add
+        const bool warp_dead = i * kBQ + quad * 32 >= N;
         mbar_wait(bar_s, ph);
         tc_fence_after();
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c = half * 32 + cc * 16;          // key column of this 16-wide chunk
           uint32_t pk[8], dsk[8];
-          if (c < ncols) {
+          if (c < ncols && !warp_dead) {
             uint32_t sv[16], dv[16];
             tmem_ld16(tm_s + lane_off + c, sv);
             tmem_ld16(tm_dp + lane_off + c, dv);
@@ -852,6 +855,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
         // dQ partial of this key block: this thread owns head dims [32*half, +32) of query row q
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
+          if (warp_dead) break;
           uint32_t v[16];
           tmem_ld16(tm_dq + lane_off + half * 32 + cc * 16, v);
           tmem_ld_wait();

@@ -52,6 +52,8 @@ struct GemmParams {
   float* colsum; // EPI 1: out_colsum[n] += sum over rows of the bf16-rounded output (bias gradient), or nullptr
   int raster;    // 1: column-persistent tile order (see decode_work): a unit keeps ONE column tile for all its tiles
   int per;       //    units per column tile in that order
+  int tail_from; // work items >= tail_from are column SUB-tiles (BN / tail_split wide) of the tiles >= tail_from:
+  int tail_split;//    the partial last wave of the static schedule is cut into 2 or 4 narrower items (1: off)
 };
 
 // EPI = 0: register-direct / smem-transposed epilogues (fp32 outputs, accumulation, BN = 192).
@@ -196,16 +198,31 @@ __device__ __forceinline__ int clc_decode(const uint4* resp) {
 //                   an epilogue warp owns the same columns throughout and accumulates their sums in registers — one
 //                   reduction per warp and kernel instead of one per warp and tile (per * 8 same-address reductions per
 //                   column instead of tiles_m * 8).  The grid is per * tiles_n units; splits = 1.
+//   tail split    : with T tiles on U units the static schedule ends in a partial wave of T % U tiles that costs a whole
+//                   tile time (M = 12608: 150 tiles of 256 x 256 on 74 pairs = 2 + 2/74 waves -> 3 tile times).  The items
+//                   of that last wave are cut into tail_split column sub-tiles each (sub = 0 .. tail_split - 1, BN /
+//                   tail_split columns: the MMA runs with a narrower N, the B box is loaded at the sub-tile's column
+//                   offset and only the epilogue warps of the first 4 / tail_split column slices have work), so the
+//                   tail costs 1/2 or 1/4 of a tile time.  sub = -1: full tile.
 __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int tiles, int nunits, int& split, int& tm,
-                                            int& tn) {
+                                            int& tn, int& sub) {
+  sub = -1;
   if (p.raster) {
     const int u = w % nunits, i = w / nunits;
     split = 0;
     tn = u % p.tiles_n;
     tm = u / p.tiles_n + i * p.per;
   } else {
-    split = w / tiles;
-    const int t = w - split * tiles;
+    int t;
+    if (w >= p.tail_from && p.tail_split > 1) {   // (splits == 1 whenever the tail is split)
+      const int j = w - p.tail_from;
+      t = p.tail_from + j / p.tail_split;
+      sub = j % p.tail_split;
+      split = 0;
+    } else {
+      split = w / tiles;
+      t = w - split * tiles;
+    }
     tm = t / p.tiles_n;
     tn = t - tm * p.tiles_n;
   }
@@ -747,7 +764,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   pdl_trigger();
 
   const int tiles = p.tiles_m * p.tiles_n;
-  const int total_work = tiles * p.splits;
+  const int total_work = p.tail_split > 1 ? p.tail_from + (tiles - p.tail_from) * p.tail_split : tiles * p.splits;
   const int kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
   const int unit = blockIdx.x / kNCta;
   const int nunits = gridDim.x / kNCta;
@@ -760,10 +777,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     for (int w = unit; w >= 0; w = ti.next(w, lane)) {
-      int split, tm, tn;
-      decode_work(p, w, tiles, nunits, split, tm, tn);
+      int split, tm, tn, sub;
+      decode_work(p, w, tiles, nunits, split, tm, tn, sub);
       const int m0 = tm * (BM * kNCta) + rank * BM;
-      const int n0 = tn * BN + rank * L::kBNH;
+      // sub-tile: the same boxes, loaded at the sub-tile's columns; the MMA reads only the first rows of each half
+      const int n0 = sub < 0 ? tn * BN + rank * L::kBNH
+                             : tn * BN + sub * (BN / p.tail_split) + rank * (BN / p.tail_split / kNCta);
       const int kb0 = split * kb_per_split;
       const int kb1 = min(p.kblocks, kb0 + kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -801,15 +820,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (leader CTA of the pair only)
     if (leader) {
-      const uint32_t idesc = umma_idesc_bf16(BM * kNCta, BN, A_MN, B_MN);
+      const uint32_t idesc_full = umma_idesc_bf16(BM * kNCta, BN, A_MN, B_MN);
+      const uint32_t idesc_sub = umma_idesc_bf16(BM * kNCta, BN / (p.tail_split > 1 ? p.tail_split : 1), A_MN, B_MN);
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = unit; w >= 0; w = ti.next(w, lane)) {
-        int split, tm_unused, tn_unused;
-        decode_work(p, w, tiles, nunits, split, tm_unused, tn_unused);
+        int split, tm_unused, tn_unused, sub;
+        decode_work(p, w, tiles, nunits, split, tm_unused, tn_unused, sub);
+        const uint32_t idesc = sub < 0 ? idesc_full : idesc_sub;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -880,21 +901,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t aux_phase = 0;
-    auto tile_origin = [&](int w, int& row0, int& col0) {
-      int split_unused, tm, tn;
-      decode_work(p, w, tiles, nunits, split_unused, tm, tn);
+    // -> false when this warp's column slice lies outside the (sub-)tile of work item w
+    auto tile_origin = [&](int w, int& row0, int& col0) -> bool {
+      int split_unused, tm, tn, sub;
+      decode_work(p, w, tiles, nunits, split_unused, tm, tn, sub);
       row0 = tm * (BM * kNCta) + rank * BM + quad * 32;
-      col0 = tn * BN + slice * kColsPerWarp;
+      col0 = tn * BN + (sub > 0 ? sub * (BN / p.tail_split) : 0) + slice * kColsPerWarp;
+      return sub < 0 || slice * p.tail_split < 4;
     };
     auto load_aux = [&](int w) {   // lane 0: aux tile of work item w -> this warp's staging buffer
       int r0, c0;
-      tile_origin(w, r0, c0);
+      if (!tile_origin(w, r0, c0)) return;
       mbar_expect_tx(&aux_bar[ew], L::kEpiWarpBytes);
       tma_load_2d(stg, &tmap_aux, &aux_bar[ew], c0, r0);
     };
     auto load_res = [&](int w, int b) {   // lane 0 (EPI = 2): fp32 residual tile of work item w -> buffer b
       int r0, c0;
-      tile_origin(w, r0, c0);
+      if (!tile_origin(w, r0, c0)) return;
       mbar_expect_tx(&aux_bar[2 * ew + b], 4096);
       tma_load_2d(stg + b * 4096, &tmap_aux, &aux_bar[2 * ew + b], c0, r0);
     };
@@ -902,24 +925,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (EPI == 1 && p.aux_mode != 0 && lane == 0) load_aux(unit);
     if (res_tma && lane == 0) load_res(unit, 0);
     int w_next = ti.next(unit, lane);   // one work item ahead: the aux / residual tile of the next item is prefetched
-    int ntile = 0;
+    int nact = 0;                       // work items in which this warp had columns to process
     float cs0 = 0.0f, cs1 = 0.0f;   // raster = 1: this lane's two column sums, carried across the warp's tiles
     int cs_col0 = -1;
-    for (int w = unit; w >= 0; w = w_next, w_next = (w >= 0 ? ti.next(w, lane) : -1), ++ntile) {
-      const int split = p.raster ? 0 : w / tiles;
+    for (int w = unit; w >= 0; w = w_next, w_next = (w >= 0 ? ti.next(w, lane) : -1)) {
+      const int split = (p.raster || p.tail_split > 1) ? 0 : w / tiles;
       int row0, col0;
-      tile_origin(w, row0, col0);
-      cs_col0 = col0;
+      const bool active = tile_origin(w, row0, col0);
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * L::kAccStride + slice * kColsPerWarp);
-      if constexpr (EPI == 2) {
-        const int b = ntile & 1;
+      if (!active) {
+        // column slice beyond a sub-tile: nothing to read, but the accumulator stage is released only once its MMAs
+        // have completed (an early arrival could otherwise be counted in the NEXT phase of tempty)
+        mbar_wait(&tfull_bar[acc], acc_phase);
+      } else if constexpr (EPI == 2) {
+        cs_col0 = col0;
+        const int b = nact & 1;
         if (res_tma && lane == 0 && w_next >= 0) {
           bulk_wait_read0();            // the previous tile's store out of the other buffer has drained it
           load_res(w_next, b ^ 1);      // lands while this tile is processed
         }
-        epilogue_tile_f32_tma<kChunks>(p, &tmap_out, stg + b * 4096, &aux_bar[2 * ew + b], (uint32_t)(ntile >> 1) & 1u, taddr,
+        epilogue_tile_f32_tma<kChunks>(p, &tmap_out, stg + b * 4096, &aux_bar[2 * ew + b], (uint32_t)(nact >> 1) & 1u, taddr,
                                        &tfull_bar[acc], acc_phase, row0, col0, lane);
       } else if constexpr (EPI == 1) {
+        cs_col0 = col0;
         epilogue_tile_bf16_tma<kChunks>(p, &tmap_out, &tmap_out2, stg, &aux_bar[ew], aux_phase, taddr, &tfull_bar[acc],
                                         acc_phase, row0, col0, split == 0, lane, cs0, cs1);
       } else if (p.out_f32) {
@@ -934,12 +962,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         else mbar_arrive_relaxed(&tempty_bar[acc]);
       }
       if (EPI == 1 && p.aux_mode != 0) {
-        aux_phase ^= 1;
+        if (active) aux_phase ^= 1;
         if (lane == 0 && w_next >= 0) {
           bulk_wait_read0();          // the store issued above has drained the buffer
           load_aux(w_next);           // lands while the MMA warp works on the next tile
         }
       }
+      if (active) ++nact;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (EPI == 1 && p.colsum != nullptr && p.raster && cs_col0 >= 0 && lane < kColsPerWarp / 2) {
@@ -1019,10 +1048,42 @@ struct TileChoice {
   int cta2, bn, splits;
 };
 
+// Number of column sub-tiles (1, 2 or 4) the `rem` tiles of the partial last wave are cut into (decode_work): sub-tile
+// widths 128 / 96 / 64; an MN-major B operand is staged in 64-column boxes, so a CTA's share must be whole boxes; every
+// unit gets at most one sub-tile (rem * S <= units).
+static bool tail_mn_partial() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VS_GEMM_TAIL_MN");   // experiment: let the MMA read part of a 64-column MN-major box
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+static int tail_split_for(int bn, int cta2, int b_mn, int rem, int units, int max_s) {
+  if (rem <= 0) return 1;
+  for (int S = max_s; S >= 2; S >>= 1) {
+    const int wsub = bn / S, per_cta = wsub / (cta2 ? 2 : 1);
+    if (wsub != 128 && wsub != 96 && wsub != 64) continue;
+    if (b_mn && per_cta % 64 != 0 && !tail_mn_partial()) continue;
+    if (rem * S > units) continue;
+    return S;
+  }
+  return 1;
+}
+static int tail_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VS_GEMM_TAIL");   // 0: off (A/B runs), 2: halves only, default 4
+    v = e ? atoi(e) : 4;
+    if (v != 0 && v != 2) v = 4;
+  }
+  return v;
+}
+
 // Cost model: a 256xBN pair tile (cta_group::2) and a 128xBN single-CTA tile take about the same time per k-block
 // (the single CTA runs at half the tensor rate), so cost ~ waves * BN * k-blocks-per-work-item.
 static TileChoice choose_tiles(int M, int N, int kblocks, int nsm, bool allow_split, int forced_split, int forced_cfg,
-                               bool allow_192) {
+                               bool allow_192, int b_mn) {
   TileChoice best{0, 256, 1};
   double best_cost = 1e30;
   const int cand[5][2] = {{1, 256}, {1, 192}, {1, 128}, {0, 256}, {0, 128}};
@@ -1044,7 +1105,12 @@ static TileChoice choose_tiles(int M, int N, int kblocks, int nsm, bool allow_sp
       // Constants fitted to the measured table of tools/gemm_bench.py over the ViT-B/16 shapes x 5 configurations
       // (r01: the first constants, overhead 6 / no width penalty, mis-picked pair128 for the QKV projection
       // (47.3 vs 42.1 us) and for the fc2 weight gradient (52.2 vs 48.2 us)).
-      double cost = double(waves) * bn * (bn == 128 ? 1.05 : 1.0) * (kb + 1.5);
+      double weff = double(waves);
+      if (s == 1 && tail_env() && work % units != 0) {   // a split last wave costs 1/S of a tile time (+ its fill / drain)
+        const int S = tail_split_for(bn, cta2, b_mn, work % units, units, tail_env());
+        if (S > 1) weff = double(work / units) + 1.0 / S + 0.1;
+      }
+      double cost = weff * bn * (bn == 128 ? 1.05 : 1.0) * (kb + 1.5);
       if (!cta2) cost *= 1.02;  // prefer pairs on ties (less L2 traffic)
       if (cost < best_cost) { best_cost = cost; best = {cta2, bn, s}; }
     }
@@ -1115,7 +1181,8 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
     epi_env = (e && strcmp(e, "direct") == 0) ? 0 : 1;
   }
   const bool want_tma = epi_env == 1 && d->out_dtype == 0;
-  TileChoice tc = choose_tiles(d->M, d->N, p.kblocks, nsm, d->accumulate != 0, d->split_k, forced_cfg, !want_tma);
+  TileChoice tc = choose_tiles(d->M, d->N, p.kblocks, nsm, d->accumulate != 0, d->split_k, forced_cfg, !want_tma,
+                                d->b_mn_major != 0);
   // fp32 outputs (+ residual) of the 128-column tiles: TMA residual prefetch + TMA store (EPI = 2)
   const bool f32_tma = epi_env == 1 && d->out_dtype == 1 && !d->accumulate && d->row_tokens == 0 && tc.bn == 128 &&
                        d->aux_mode == 0 && d->out2 == nullptr && d->ldo % 4 == 0 && (d->residual == nullptr || d->ldr % 4 == 0);
@@ -1140,7 +1207,6 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
   p.out2 = (__nv_bfloat16*)d->out2; p.ldo2 = d->ldo2;
   p.aux = (const __nv_bfloat16*)d->aux; p.ldaux = d->ldaux; p.aux_mode = d->aux_mode;
   p.residual = d->residual; p.ldr = d->ldr; p.row_tokens = d->row_tokens;
-  p.colsum = nullptr;
   p.drop.thresh = 0; p.drop.scale = 1.0f; p.drop.seed = nullptr; p.drop.site = 0;
   if (d->dropout_p > 0.0f) {
     VS_CHECK_ARG(d->dropout_p < 1.0f && d->dropout_seed != nullptr && d->out_dtype == 1 && !d->accumulate,
@@ -1230,15 +1296,35 @@ extern "C" int vs_gemm_bf16(const vs_gemm_desc* d, void* stream) {
       units_eff = per * p.tiles_n;
     }
   }
+  // partial last wave of the static schedule -> narrower work items (decode_work).  Every unit gets at most ONE sub-tile,
+  // as its last item (rem * S <= units), which the epilogue's prefetch logic relies on.  Sub-tile widths 128 / 96 / 64;
+  // an MN-major B operand is staged in 64-column boxes, so a CTA's share of the sub-tile must be whole boxes
+  // (tail_split_for).  VS_GEMM_TAIL=0 switches it off (A/B runs), =2 limits the split to halves.
+  p.tail_from = total;
+  p.tail_split = 1;
+  int total_items = total;
+  {
+    const int units = tc.cta2 ? nsm / 2 : nsm;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int rem = tiles % units;
+    if (tail_env() && splits == 1 && !p.dynamic && !p.raster && rem > 0) {
+      const int S = tail_split_for(BN, tc.cta2, d->b_mn_major != 0, rem, units, tail_env());
+      if (S > 1) {
+        p.tail_split = S;
+        p.tail_from = tiles - rem;
+        total_items = p.tail_from + rem * S;
+      }
+    }
+  }
   int rc = 0;
   if (tc.cta2) {
     const int pairs = nsm / 2;
-    const int grid = p.raster ? 2 * units_eff : (p.dynamic ? 2 * total : 2 * (total < pairs ? total : pairs));
+    const int grid = p.raster ? 2 * units_eff : (p.dynamic ? 2 * total : 2 * (total_items < pairs ? total_items : pairs));
     if (BN == 256) rc = launch_epi<256, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     else if (BN == 192) rc = launch_major<192, 1, 0>(d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     else rc = launch_epi<128, 1>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
   } else {
-    const int grid = p.raster ? units_eff : (p.dynamic ? total : (total < nsm ? total : nsm));
+    const int grid = p.raster ? units_eff : (p.dynamic ? total : (total_items < nsm ? total_items : nsm));
     if (BN == 256) rc = launch_epi<256, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
     else rc = launch_epi<128, 0>(epi, d->a_mn_major, d->b_mn_major, ta, tb, om, p, grid, st);
   }

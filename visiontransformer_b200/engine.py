@@ -90,7 +90,7 @@ class Engine:
         self.launches = 0            # kernel launches issued by the last forward/backward (for bench bookkeeping)
         self._two_streams = os.environ.get("VS_BWD_STREAMS", "1") == "2"   # opt-in: measured neutral (11.03-11.10 vs 11.05 ms/step, r02)
         self._side = None
-        self._fuse_colsum = os.environ.get("VS_FUSE_COLSUM", "0") == "1"
+        self._fuse_colsum = os.environ.get("VS_FUSE_COLSUM", "1") != "0"   # A/B switch: 0 = separate column-sum pass
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -476,9 +476,10 @@ class Engine:
             # LayerNorm backward that produced dx16)
             fork()
             wgrad(ws["dx16"], ws["h_act"][i], self.g32(p + "output.dense.weight"))
-            # VS_FUSE_COLSUM=1: the fc1 bias gradient (column sums of dh) comes out of this GEMM's epilogue (out_colsum,
-            # column-persistent tile order); default: a separate column-sum pass.  Measured -0.1 ms per step for the fused
-            # form, inside the box-to-box variation, while the GEMM kernel then carries non-GEMM work (r02 A/B logs)
+            # the fc1 bias gradient (column sums of dh) comes out of this GEMM's epilogue (out_colsum, column-persistent
+            # tile order: sums carried in registers, one reduction per warp and kernel).  r02 session 13, same box:
+            # 11.46 -> 11.24 ms per step, 12 launches and a 77 MB re-read per layer gone; VS_FUSE_COLSUM=0 restores the
+            # separate column-sum pass
             K.gemm(ws["dx16"], self.w16(p + "output.dense.weight"), ws["dh"], b_mn=True, aux=ws["h_pre"][i],
                    aux_mode=K.AUX_GELU_GRAD,
                    colsum=self.g32(p + "intermediate.dense.bias") if self._fuse_colsum else None)
