@@ -126,8 +126,11 @@ int vs_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, const fl
  *   qkv  bf16 [B, N, 3, H, 64]  (fused projection output; head_dim must be 64)
  *   ctx  bf16 [B, N, H, 64]
  *   lse  fp32 [B, H, N]  natural-log row logsumexp of the scaled scores (saved for backward; may be NULL)
- * Backward: dctx bf16 [B,N,H,64] -> dqkv bf16 [B,N,3,H,64].  dq_accum is an fp32 [B,N,H,64] scratch,
- *   delta an fp32 [B,H,N] scratch; both caller-provided.
+ * Backward: dctx bf16 [B,N,H,64] -> dqkv bf16 [B,N,3,H,64].  delta is an fp32 [B,H,N] scratch (caller-provided).
+ *   dq_accum != NULL: fp32 [B,N,H,64] scratch that RECEIVES dQ (the Q slot of dqkv is left untouched: the caller
+ *     rounds dq_accum into it, e.g. with vs_colsum_cast_bf16) — any N.
+ *   dq_accum == NULL: N <= 256 only; all three slots of dqkv are written as bf16 by a kernel that keeps whole
+ *     (batch, head) items on one SM (no fp32 atomics, no cast pass).
  * dropout_p > 0 drops attention probabilities (attention_probs_dropout_prob, SDPA dropout_p) with a counter-based
  *   mask regenerated identically in backward.
  * ------------------------------------------------------------------------------------------------ */

@@ -119,6 +119,11 @@ def test_attention_dropout_forward_backward(B, N, H):
     assert _rel(dqkv[:, :, 1].permute(0, 2, 1, 3), k.grad) < 2e-2
     assert _rel(dqkv[:, :, 2].permute(0, 2, 1, 3), v.grad) < 2e-2
     assert _rel(dq_acc.view(B, N, H, 64).permute(0, 2, 1, 3), q.grad) < 2e-2
+    if N <= 256:   # short-sequence kernel (dq_accum = None): same masks, all three gradients as bf16
+        dqkv2 = torch.full_like(dqkv, float("nan"))
+        K.attention_bwd(qkv, ctx, dctx, lse, dqkv2, None, delta, B, N, H, 0.125, dropout=drop)
+        for i, g in enumerate((q.grad, k.grad, v.grad)):
+            assert _rel(dqkv2[:, :, i].permute(0, 2, 1, 3), g) < 2e-2
 
 
 def test_module_train_eval_dropout_semantics():

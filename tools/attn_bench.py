@@ -38,4 +38,6 @@ for p in (0.0, 0.1):
     drop = (p, seed, 1000) if p > 0 else None
     t(f"fwd p={p}", lambda: K.attention_fwd(qkv, ctx, lse, B, N, H, 0.125, dropout=drop))
     t(f"bwd p={p}", lambda: K.attention_bwd(qkv, ctx, dctx, lse, dqkv, dq_acc, delta, B, N, H, 0.125, dropout=drop))
+    if N <= 256:
+        t(f"bwd (short kernel) p={p}", lambda: K.attention_bwd(qkv, ctx, dctx, lse, dqkv, None, delta, B, N, H, 0.125, dropout=drop))
 t("reference: layernorm_fwd (58 MB)", lambda: K.layernorm_fwd(x, g, g, 1e-12, y_bf16=y16))

@@ -274,10 +274,19 @@ def probe_attn():
             report(f"attn bwd dK B{Bn} N{N} H{H}", rel(dqkv[:, :, 1].permute(0, 2, 1, 3), k.grad), 2e-2)
             report(f"attn bwd dV B{Bn} N{N} H{H}", rel(dqkv[:, :, 2].permute(0, 2, 1, 3), v.grad), 2e-2)
             report(f"attn bwd dQ B{Bn} N{N} H{H}", rel(dq_acc.view(Bn, N, H, 64).permute(0, 2, 1, 3), q.grad), 2e-2)
+            if N <= 256:
+                # short-sequence kernel: whole (batch, head) items per CTA, all three gradients written as bf16
+                dqkv2 = torch.full_like(dqkv, float("nan"))
+                K.attention_bwd(qkv, ctx, dctx, lse, dqkv2, None, delta, Bn, N, H, 0.125)
+                for i, (nm, ref_g) in enumerate((("dQ", q.grad), ("dK", k.grad), ("dV", v.grad))):
+                    report(f"attn bwd (short) {nm} B{Bn} N{N} H{H}", rel(dqkv2[:, :, i].permute(0, 2, 1, 3), ref_g), 2e-2)
         run(f"attn {Bn} {N} {H}", f)
 
     case(1, 128, 1)
     case(2, 197, 12)
+    case(40, 197, 12)    # 480 items on 148 SMs: several items per CTA (buffer hand-over between items), ragged last round
+    case(7, 130, 3)
+    case(5, 100, 2)      # one query tile
     case(1, 64, 2)
     case(2, 256, 2)      # largest single-pass forward
     case(1, 17, 1)

@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvitseg.so")
+# VS_LIB_PATH: load another build of the same library (A/B runs of kernel variants on one box)
+LIB_PATH = os.environ.get("VS_LIB_PATH") or os.path.join(_HERE, "lib", "libvitseg.so")
 
 _lib = None
 

@@ -570,7 +570,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // also clears the dQ accumulators of this warp's 32 rows (layout [B, N, H, 64] = row * 64; 8 KB contiguous per warp,
   // 512 B per store instruction): saves the separate memset launch
-  {
+  if (dq_accum != nullptr) {
     const long long total4 = (long long)B * N * H * (kDH / 4);
     const long long w0 = (row - (threadIdx.x & 31)) * (kDH / 4);
     float4* z = reinterpret_cast<float4*>(dq_accum);
@@ -901,6 +901,384 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
   if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
 
+// ================================================================================================
+// backward, short sequences (N <= 256: every 224x224 / patch-16 configuration)
+// ================================================================================================
+// One persistent CTA per SM, work item = (batch, head): ALL keys and queries of the head are resident in shared memory
+// (K, V: 4 blocks of 64 keys; Q, dO: 128-row tiles), so dQ, dK and dV are complete inside the CTA — no fp32 atomics into
+// a scratch, no zero-fill of that scratch, no cast pass afterwards (the key-block kernel above issues 155 MB of
+// red.global.add per layer at N = 197 and needs a 39 MB memset + a 39 MB re-read around it).
+//   steps (kb, qt) = (64-key block, 128-query tile), kb outer, the query-tile order flipping with kb:
+//     S = Q_qt K_kb^T, dP = dO_qt V_kb^T             -> TMEM, double-buffered by step parity
+//     P = exp2(S c - lse), dS = P (dP - delta) scale  -> bf16 shared memory, double-buffered by step parity
+//     dQ_qt += dS K_kb        (TMEM, accumulates over kb: read out once per item)
+//     dV_kb += P^T dO_qt, dK_kb += dS^T Q_qt          (TMEM, accumulate over qt: read out once per key block)
+//   TMEM (512 columns): S0 | dP0 | S1 | dP1 | dQ_0 | dQ_1 | dK | dV, 64 columns each.
+// Warps: 0-7 / 8-15 two compute groups — group g owns the steps of parity g, so one group's exp / dS phase overlaps the
+// other group's MMAs (the two-CTAs-per-SM overlap of the key-block kernel, inside one CTA); 16-19 read out dK / dV /
+// dQ (one per TMEM lane quadrant) while the compute groups continue; 20 issues the MMAs; 21 drives TMA.  The next
+// item's K / V blocks and query tiles are loaded as soon as the current item's last MMA on that buffer has retired
+// (per-buffer mbarriers; a third Q / dO slot holds the next item's first query tile).
+struct AttnBwdShortSmem {
+  static constexpr int kK = 0;                       // 4 x (64 x 128 B)
+  static constexpr int kV = 32768;
+  static constexpr int kQ = 65536;                   // 3 slots x (128 x 128 B)
+  static constexpr int kDO = kQ + 3 * 16384;
+  static constexpr int kP = kDO + 3 * 16384;         // 2 x (128 x 128 B)
+  static constexpr int kDS = kP + 2 * 16384;
+  static constexpr int kBar = kDS + 2 * 16384;
+  static constexpr int kTotal = kBar + 512 + 1024;
+};
+static_assert(AttnBwdShortSmem::kTotal <= 227 * 1024, "attention backward (short): shared memory budget");
+constexpr int kBwdShortThreads = 22 * 32;
+
+__global__ void __launch_bounds__(kBwdShortThreads, 1)
+attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_constant__ CUtensorMap tmap_q,
+                      const __grid_constant__ CUtensorMap tmap_do, const float* __restrict__ lse,
+                      const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int B, int N, int H,
+                      float scale, const DropCfg drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdShortSmem::kBar);
+  uint64_t* kfull = bars + 0;     // [4] K / V block landed
+  uint64_t* kfree = bars + 4;     // [4] last MMA reading the block retired
+  uint64_t* qfull = bars + 8;     // [3] Q / dO slot landed
+  uint64_t* qfree = bars + 11;    // [3]
+  uint64_t* sfull = bars + 14;    // [2] S / dP of a step complete
+  uint64_t* pfull = bars + 16;    // [2] P / dS of a step in shared memory (256 arrivals); S / dP consumed
+  uint64_t* pfree = bars + 18;    // [2] the MMAs reading P / dS retired
+  uint64_t* kvfull = bars + 20;   // dK / dV of a key block complete
+  uint64_t* kvfree = bars + 21;   // ... and read out (4 arrivals)
+  uint64_t* dqfull = bars + 22;   // dQ of the item complete
+  uint64_t* dqfree = bars + 23;   // ... and read out (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * kDH;
+  const int nq = (N + kBQ - 1) / kBQ;      // 1 or 2
+  const int nkb = (N + kKB - 1) / kKB;     // 1 .. 4
+  const int nsteps = nq * nkb;
+  const int total = B * H;
+
+  if (warp == 20) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_kv);
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_do);
+      for (int i = 0; i < 4; ++i) { mbar_init(&kfull[i], 1); mbar_init(&kfree[i], 1); }
+      for (int i = 0; i < 3; ++i) { mbar_init(&qfull[i], 1); mbar_init(&qfree[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pfull[i], 256); mbar_init(&pfree[i], 1); }
+      mbar_init(kvfull, 1);
+      mbar_init(kvfree, 4);
+      mbar_init(dqfull, 1);
+      mbar_init(dqfree, 4);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  // step s of an item -> key block, position inside the block's query loop, query tile (order flips with kb so that
+  // both step parities — both compute groups — see the full first and the partly empty second query tile in turn)
+  auto decode = [&](int s, int& kb, int& j, int& qt) {
+    kb = nq == 2 ? (s >> 1) : s;
+    j = nq == 2 ? (s & 1) : 0;
+    qt = (kb & 1) ? nq - 1 - j : j;
+  };
+  // query tile 1 always lives in slot 1; tile 0 alternates between slots 0 and 2 so that the NEXT item's first tile
+  // can land while the current item still reads its own
+  auto qslot = [&](int it, int qt) { return qt == 1 ? 1 : ((it & 1) ? 2 : 0); };
+  auto quse = [&](int it, int sl) { return sl == 1 ? it : (it >> 1); };   // how often the slot was used before item it
+
+  if (warp == 21) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int h = w % H, b = w / H;
+        auto load_kv = [&](int kb) {
+          if (it > 0) mbar_wait(&kfree[kb], (uint32_t)(it - 1) & 1u);
+          mbar_expect_tx(&kfull[kb], 2 * 8192);
+          tma_load_3d(smem + AttnBwdShortSmem::kK + kb * 8192, &tmap_kv, &kfull[kb], D + h * kDH, kb * kKB, b);
+          tma_load_3d(smem + AttnBwdShortSmem::kV + kb * 8192, &tmap_kv, &kfull[kb], 2 * D + h * kDH, kb * kKB, b);
+        };
+        auto load_q = [&](int qt) {
+          const int sl = qslot(it, qt), u = quse(it, sl);
+          if (u > 0) mbar_wait(&qfree[sl], (uint32_t)(u - 1) & 1u);
+          mbar_expect_tx(&qfull[sl], 2 * 16384);
+          tma_load_3d(smem + AttnBwdShortSmem::kQ + sl * 16384, &tmap_q, &qfull[sl], h * kDH, qt * kBQ, b);
+          tma_load_3d(smem + AttnBwdShortSmem::kDO + sl * 16384, &tmap_do, &qfull[sl], h * kDH, qt * kBQ, b);
+        };
+        load_kv(0);
+        for (int qt = 0; qt < nq; ++qt) load_q(qt);
+        for (int kb = 1; kb < nkb; ++kb) load_kv(kb);
+      }
+    }
+  } else if (warp == 20) {
+    // ---------------------------------------------------------------- MMA issuer (converged warp, elected lane)
+    // one descriptor low word per operand and layout; offsets are added in 16-byte units (umma_desc_lo)
+    const uint32_t aK = smem_u32(smem + AttnBwdShortSmem::kK), aV = smem_u32(smem + AttnBwdShortSmem::kV);
+    const uint32_t aQ = smem_u32(smem + AttnBwdShortSmem::kQ), aDO = smem_u32(smem + AttnBwdShortSmem::kDO);
+    const uint32_t aP = smem_u32(smem + AttnBwdShortSmem::kP), aDS = smem_u32(smem + AttnBwdShortSmem::kDS);
+    const uint32_t kQ_k = umma_desc_lo(aQ, 16), kK_k = umma_desc_lo(aK, 16), kDO_k = umma_desc_lo(aDO, 16),
+                   kV_k = umma_desc_lo(aV, 16), kDS_k = umma_desc_lo(aDS, 16);                  // K-major
+    const uint32_t kK_mn = umma_desc_lo(aK, 16384), kDO_mn = umma_desc_lo(aDO, 16384), kQ_mn = umma_desc_lo(aQ, 16384),
+                   kP_mn = umma_desc_lo(aP, 16384), kDS_mn = umma_desc_lo(aDS, 16384);          // MN-major
+    constexpr uint32_t kSlot = 16384 >> 4, kBlk = 8192 >> 4, kStep16 = 2048 >> 4;   // Q / dO slot (= P / dS buffer), K / V block, 16 rows
+    const uint32_t id_dq = umma_idesc_bf16(kBQ, kDH, 0, 1), id_dkv = umma_idesc_bf16(kKB, kDH, 1, 1);
+    const uint32_t id_s_full = umma_idesc_bf16(kBQ, kKB, 0, 0);
+    const int ncols_tail = (N - (nkb - 1) * kKB + 15) & ~15;
+    const uint32_t id_s_tail = umma_idesc_bf16(kBQ, ncols_tail, 0, 0);
+    const uint32_t tm_dq = tmem_base + 256, tm_dk = tmem_base + 384, tm_dv = tmem_base + 448;
+    int it = 0;
+    uint32_t g = 0;   // steps issued so far by this CTA: buffer = g & 1, use count of the buffer = g >> 1
+    auto issue_sdp = [&](int it_, int s, uint32_t gs) {   // S / dP of step s of this CTA's item number it_
+      int kb, j, qt;
+      decode(s, kb, j, qt);
+      const int sl = qslot(it_, qt);
+      mbar_wait(&kfull[kb], (uint32_t)it_ & 1u);
+      mbar_wait(&qfull[sl], (uint32_t)quse(it_, sl) & 1u);
+      tc_fence_after();
+      const uint32_t idesc = kb == nkb - 1 ? id_s_tail : id_s_full;
+      const uint32_t qd = kQ_k + sl * kSlot, kd = kK_k + kb * kBlk, od = kDO_k + sl * kSlot, vd = kV_k + kb * kBlk;
+      const uint32_t tm_s = tmem_base + (gs & 1u) * 128u, tm_dp = tm_s + 64u;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kDH / 16; ++k) umma_bf16_lo(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
+#pragma unroll
+        for (int k = 0; k < kDH / 16; ++k) umma_bf16_lo(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
+        umma_commit(&sfull[gs & 1u]);
+      }
+      __syncwarp();
+    };
+    // S / dP run up to two steps ahead of the gradient MMAs (one per TMEM buffer), across item boundaries too: the
+    // buffer of step gs + 2 is the one step gs has just handed back with its P / dS.  A step further ahead than the
+    // very next one is only issued if its operands have already landed (its K block / query slot may still be
+    // waiting for a commit that follows in program order: blocking there would deadlock); the very next step only
+    // depends on steps that have been committed and may be waited for.
+    struct Pos { int it, s, w; };
+    auto next_pos = [&](Pos p) {
+      if (p.s + 1 < nsteps) return Pos{p.it, p.s + 1, p.w};
+      return Pos{p.it + 1, 0, p.w + (int)gridDim.x};
+    };
+    auto operands_ready = [&](const Pos& p) {
+      int kb, j, qt;
+      decode(p.s, kb, j, qt);
+      const int sl = qslot(p.it, qt);
+      return mbar_test_wait(&kfull[kb], (uint32_t)p.it & 1u) && mbar_test_wait(&qfull[sl], (uint32_t)quse(p.it, sl) & 1u);
+    };
+    Pos ahead{0, 0, (int)blockIdx.x};   // next step whose S / dP have not been issued yet
+    uint32_t g_ahead = 0;
+    auto issue_ahead = [&]() {
+      issue_sdp(ahead.it, ahead.s, g_ahead++);
+      ahead = next_pos(ahead);
+    };
+    if (ahead.w < total) issue_ahead();
+    if (ahead.w < total && operands_ready(ahead)) issue_ahead();
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      for (int s = 0; s < nsteps; ++s) {
+        int kb, j, qt;
+        decode(s, kb, j, qt);
+        const uint32_t gs = g + s, bsel = gs & 1u;
+        const int sl = qslot(it, qt);
+        const int nk16 = (kb == nkb - 1 ? ncols_tail : kKB) >> 4;
+        mbar_wait(&pfull[bsel], (gs >> 1) & 1u);
+        while (ahead.w < total && g_ahead <= gs + 2 && operands_ready(ahead)) issue_ahead();
+        if (s == 0 && it > 0) mbar_wait(dqfree, (uint32_t)(it - 1) & 1u);   // the previous item's dQ has been read out
+        tc_fence_after();
+        const uint32_t ds_k = kDS_k + bsel * kSlot, k_mn = kK_mn + kb * kBlk;
+        const uint32_t p_mn = kP_mn + bsel * kSlot, ds_mn = kDS_mn + bsel * kSlot;
+        const uint32_t do_mn = kDO_mn + sl * kSlot, q_mn = kQ_mn + sl * kSlot;
+        if (elect_one()) {
+          // dQ_qt (+)= dS K_kb : A = dS K-major (M = 128 queries, K = keys), B = K_kb MN-major (N = 64)
+          for (int kk = 0; kk < nk16; ++kk)
+            umma_bf16_lo(tm_dq + qt * 64, ds_k + 2 * kk, k_mn + kk * kStep16, id_dq, (kb > 0 || kk > 0));
+        }
+        __syncwarp();
+        if (j == 0) {
+          const int ckv = it * nkb + kb;   // key blocks completed so far
+          if (ckv > 0) {
+            mbar_wait(kvfree, (uint32_t)(ckv - 1) & 1u);   // dK / dV of the previous key block have been read out
+            tc_fence_after();
+          }
+        }
+        if (elect_one()) {
+          // dV_kb (+)= P^T dO_qt, dK_kb (+)= dS^T Q_qt : A read MN-major (M = 64 keys, K = 128 queries), B MN-major
+#pragma unroll
+          for (int kk = 0; kk < kBQ / 16; ++kk)
+            umma_bf16_lo(tm_dv, p_mn + kk * kStep16, do_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < kBQ / 16; ++kk)
+            umma_bf16_lo(tm_dk, ds_mn + kk * kStep16, q_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
+          umma_commit(&pfree[bsel]);
+          if (j == nq - 1) {
+            umma_commit(kvfull);
+            umma_commit(&kfree[kb]);
+          }
+          if (kb == nkb - 1) umma_commit(&qfree[sl]);
+          if (s == nsteps - 1) umma_commit(dqfull);
+        }
+        __syncwarp();
+        if (ahead.w < total && g_ahead == gs + 1) issue_ahead();   // the next step must be under way: wait for its loads
+      }
+      g += (uint32_t)nsteps;
+    }
+  } else if (warp >= 16) {
+    // ---------------------------------------------------------------- read-out warps (one per TMEM lane quadrant)
+    const int quad = warp & 3;
+    const uint32_t lane_off = uint32_t(quad * 32) << 16;
+    const uint32_t tm_dq = tmem_base + 256, tm_dk = tmem_base + 384, tm_dv = tmem_base + 448;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int h = w % H, b = w / H;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int ckv = it * nkb + kb;
+        mbar_wait(kvfull, (uint32_t)ckv & 1u);
+        tc_fence_after();
+        // M = 64 accumulators: lanes 0-15 of quadrant `quad` hold keys 16 * quad .. + 15 of the block
+        const int kv = kb * kKB + quad * 16 + lane;
+        const bool kv_ok = lane < 16 && kv < N;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t src = which == 0 ? tm_dk : tm_dv;
+          __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (which == 0 ? D : 2 * D) + h * kDH;
+#pragma unroll
+          for (int c = 0; c < kDH; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(src + lane_off + c, v);
+            tmem_ld_wait();
+            if (kv_ok) {
+              u32x8 o;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) o.v[jj] = pack_bf16(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
+              st_global_256(dst + c, o);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(kvfree);
+      }
+      mbar_wait(dqfull, (uint32_t)it & 1u);
+      tc_fence_after();
+      for (int qt = 0; qt < nq; ++qt) {
+        const int q = qt * kBQ + quad * 32 + lane;
+        if (qt * kBQ + quad * 32 >= N) break;   // warp-uniform: no live query row in this quadrant
+        __nv_bfloat16* dst = dqkv + ((size_t)b * N + q) * (3 * D) + h * kDH;
+#pragma unroll
+        for (int c = 0; c < kDH; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tm_dq + qt * 64 + lane_off + c, v);
+          tmem_ld_wait();
+          if (q < N) {
+            u32x8 o;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) o.v[jj] = pack_bf16(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
+            st_global_256(dst + c, o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dqfree);
+    }
+  } else {
+    // ---------------------------------------------------------------- compute warps: group = step parity
+    const int grp = warp >> 3, quad = warp & 3, half = (warp >> 2) & 1;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = uint32_t(quad * 32) << 16;
+    uint8_t* sP = smem + AttnBwdShortSmem::kP + grp * 16384;
+    uint8_t* sDS = smem + AttnBwdShortSmem::kDS + grp * 16384;
+    const uint32_t tm_s = tmem_base + (uint32_t)grp * 128u, tm_dp = tm_s + 64u;
+    const float sl2 = scale * kLog2e;
+    const uint32_t dseed0 = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
+    uint32_t g = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      // per-row statistics of both query tiles (rows beyond the sequence: lse = +inf -> exp2(s - lse) = 0)
+      float lse2[2] = {INFINITY, INFINITY}, dlt[2] = {0.0f, 0.0f};
+#pragma unroll
+      for (int qt = 0; qt < 2; ++qt) {
+        const int q = qt * kBQ + r;
+        if (qt < nq && q < N) {
+          const size_t o = (size_t)w * N + q;   // (b * H + h) * N + q
+          lse2[qt] = lse[o] * kLog2e;
+          dlt[qt] = delta[o];
+        }
+      }
+      const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)w, dseed0) : 0u;   // per (batch, head)
+      for (int s = 0; s < nsteps; ++s) {
+        const uint32_t gs = g + s;
+        if ((int)(gs & 1u) != grp) continue;
+        const uint32_t u = gs >> 1;
+        int kb, j, qt;
+        decode(s, kb, j, qt);
+        const int kv0 = kb * kKB;
+        const int nvalid_kv = min(kKB, N - kv0);
+        const int ncols = (nvalid_kv + 15) & ~15;
+        const bool tail_block = nvalid_kv < kKB;
+        const int q = qt * kBQ + r;
+        const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
+        const float l2 = qt == 0 ? lse2[0] : lse2[1], dl = qt == 0 ? dlt[0] : dlt[1];
+        const bool warp_dead = qt * kBQ + quad * 32 >= N;   // no live query row in this warp: P = dS = 0
+        mbar_wait(&sfull[grp], u & 1u);
+        if (u > 0) mbar_wait(&pfree[grp], (u - 1) & 1u);   // the MMAs of this buffer's previous step have read P / dS
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 32 + cc * 16;          // key column of this 16-wide chunk
+          uint32_t pk[8], dsk[8];
+          if (c < ncols && !warp_dead) {
+            uint32_t sv[16], dv[16];
+            tmem_ld16(tm_s + lane_off + c, sv);
+            tmem_ld16(tm_dp + lane_off + c, dv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+              bool keep[2] = {true, true};
+              if (drop.thresh != 0u)
+                drop_keep2(2u * (drow + (uint32_t)((kv0 + c + k) >> 1)), dseed, drop.thresh, keep[0], keep[1]);
+              float pdv[2], dsv[2];
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                float pv = ex2_approx(__uint_as_float(sv[k + t]) * sl2 - l2);
+                if (tail_block) pv = (c + k + t < nvalid_kv) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
+                // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
+                const float mk = keep[t] ? dscale : 0.0f;
+                pdv[t] = pv * mk;
+                dsv[t] = (pv * scale) * (__uint_as_float(dv[k + t]) * mk - dl);
+              }
+              pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
+              dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { pk[k] = 0u; dsk[k] = 0u; }
+          }
+          const uint32_t slot = uint32_t(c >> 3);     // 16-byte slot inside the 128-byte (64-key) row
+          *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot)) = make_uint4(dsk[0], dsk[1], dsk[2], dsk[3]);
+          *reinterpret_cast<uint4*>(sDS + sw128_offset(r, slot + 1)) = make_uint4(dsk[4], dsk[5], dsk[6], dsk[7]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&pfull[grp]);
+      }
+      g += (uint32_t)nsteps;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 20) tmem_dealloc(tmem_base, 512);
+}
+
 static int make_tok_tmap(CUtensorMap* m, const void* base, int B, int N, int row_elems, int box_rows = 128) {
   uint64_t dims[3] = {(uint64_t)row_elems, (uint64_t)N, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)row_elems * 2, (uint64_t)N * row_elems * 2};
@@ -989,7 +1367,10 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
 extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                                 float* dq_accum, float* delta, int32_t B, int32_t N, int32_t H, float scale,
                                 float dropout_p, const uint32_t* dropout_seed, uint32_t dropout_site, void* stream) {
-  VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && dq_accum && delta, "vs_attention_bwd: null pointer");
+  VS_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && delta, "vs_attention_bwd: null pointer");
+  VS_CHECK_ARG(dq_accum != nullptr || N <= 256,
+               "vs_attention_bwd: N=%d > 256 needs the fp32 dQ accumulator (dq_accum); without it dQ is written as bf16 "
+               "by the short-sequence kernel", N);
   VS_CHECK_ARG(((uintptr_t)ctx % 32 == 0) && ((uintptr_t)dctx % 32 == 0) && ((uintptr_t)dqkv % 32 == 0) &&
                    ((uintptr_t)dq_accum % 16 == 0),
                "vs_attention_bwd: ctx / dctx / dqkv must be 32-byte aligned, dq_accum 16-byte aligned");
@@ -1017,6 +1398,21 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
     const long long rows = (long long)B * N * H;
     launch_k(attn_delta_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), (size_t)(0), st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, delta, dq_accum, B, N, H);
     VS_CHECK_LAUNCH();
+  }
+  if (dq_accum == nullptr) {
+    // short sequences: one persistent CTA per SM owns whole (batch, head) items; dQ leaves as bf16 in dqkv
+    static bool attr_s = false;
+    if (!attr_s) {
+      VS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnBwdShortSmem::kTotal));
+      attr_s = true;
+    }
+    const long long bh = (long long)B * H;
+    const int nsm_s = sm_count();
+    const unsigned grid_s = (unsigned)(bh < nsm_s ? bh : nsm_s);
+    launch_k(attn_bwd_short_kernel, dim3(grid_s), dim3(kBwdShortThreads), (size_t)(AttnBwdShortSmem::kTotal), st, tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, B, N, H, scale, dc);
+    VS_CHECK_LAUNCH();
+    return 0;
   }
   const long long items = (long long)B * H * ((N + kKB - 1) / kKB);
   VS_CHECK_ARG(items < (1LL << 31), "vs_attention_bwd: too many (batch, head, key block) work items");

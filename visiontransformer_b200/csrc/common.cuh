@@ -229,11 +229,40 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Potentially blocking probe.  The suspend-time hint lets the hardware park the thread until the phase completes (or
+// the hint expires) instead of answering "not yet" after a few dozen cycles: ncu r02 (short attention backward) showed
+// 47 % of all executed instructions in try_wait poll loops of waiting warps (one poll per ~50 cycles and warp, six
+// instructions each), taking issue slots from the warps that had work.
+#ifndef VS_MBAR_SUSPEND_NS
+#define VS_MBAR_SUSPEND_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if VS_MBAR_SUSPEND_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VS_MBAR_SUSPEND_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
+  return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time before it answers)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -350,6 +379,26 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   MN-major : a row is one K index, the 128 bytes run along M/N (64 elements).  SBO = 1024 (next 8 K rows);
 //              LBO = byte distance between consecutive 64-element M/N blocks.  Advancing K by 16 = +2048 bytes.
 // ----------------------------------------------------------------------------------------------
+// The low word of a SWIZZLE_128B / SBO = 1024 descriptor (start address and LBO); its high word is the constant
+// kUmmaDescHiSw128.  A byte offset (multiple of 16, inside the 256 KB shared-memory window) is applied by ADDING
+// offset >> 4 to the low word, so an issuing thread that precomputes one low word per operand spends one add per
+// descriptor instead of the shift / mask / or chain of umma_desc_sw128 (ncu r02: the single MMA-issuing warp of the short
+// attention backward executed ~590 instructions per step, 10 per descriptor pair, and was the kernel's critical path).
+constexpr uint32_t kUmmaDescHiSw128 = 0x40004040u;   // SBO 1024 >> 4 | version 1 << 14 | SWIZZLE_128B << 29
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
+      : "memory");
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);

@@ -91,6 +91,7 @@ class Engine:
         self._two_streams = os.environ.get("VS_BWD_STREAMS", "1") == "2"   # opt-in: measured neutral (11.03-11.10 vs 11.05 ms/step, r02)
         self._side = None
         self._fuse_colsum = os.environ.get("VS_FUSE_COLSUM", "1") != "0"   # A/B switch: 0 = separate column-sum pass
+        self._attn_bwd_short = os.environ.get("VS_ATTN_BWD", "short") != "blocks"   # A/B switch: key-block kernel always
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -501,13 +502,19 @@ class Engine:
             wgrad(ws["dx16"], ws["ctx"][i], self.g32(p + "attention.output.dense.weight"))
             K.gemm(ws["dx16"], self.w16(p + "attention.output.dense.weight"), ws["dctx"], b_mn=True)
             # attention core
-            K.attention_bwd(ws["qkv"][i], ws["ctx"][i], ws["dctx"], ws["lse"][i], ws["dqkv"], ws["dq_acc"], ws["delta"],
+            # T1 <= 256: whole (batch, head) items per CTA, dQ written as bf16 (no fp32 accumulator, no cast pass);
+            # longer sequences: key-block kernel + fp32 dQ accumulator, cast inside the bias-gradient pass below
+            short = self._attn_bwd_short and T1 <= 256
+            K.attention_bwd(ws["qkv"][i], ws["ctx"][i], ws["dctx"], ws["lse"][i], ws["dqkv"],
+                            None if short else ws["dq_acc"], ws["delta"],
                             B, T1, H, scale, dropout=self._site(p_att, 1000 + i))
-            # fused QKV projection; its bias gradient (column sums of dQKV) and the bf16 copy of the fp32 dQ
-            # accumulator come out of one pass
+            # fused QKV projection; its bias gradient = column sums of dQKV
             gw, gb = self.fused_qkv(i, arena="grads")
             wqkv, _ = self.fused_qkv(i)
-            K.colsum_cast(ws["dqkv"], ws["dq_acc"], gb, accumulate=True)
+            if short:
+                K.colsum(ws["dqkv"], gb, accumulate=True)
+            else:
+                K.colsum_cast(ws["dqkv"], ws["dq_acc"], gb, accumulate=True)
             fork()   # dqkv is final
             wgrad(ws["dqkv"], ws["ln1"][i], gw)
             K.gemm(ws["dqkv"], wqkv, ws["d_ln"], b_mn=True)
