@@ -913,7 +913,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
 //     P = exp2(S c - lse), dS = P (dP - delta) scale  -> bf16 shared memory, double-buffered by step parity
 //     dQ_qt += dS K_kb        (TMEM, accumulates over kb: read out once per item)
 //     dV_kb += P^T dO_qt, dK_kb += dS^T Q_qt          (TMEM, accumulate over qt: read out once per key block)
-//   TMEM (512 columns): S0 | dP0 | S1 | dP1 | dQ_0 | dQ_1 | dK | dV, 64 columns each.
+//   dK and dV come out of ONE M = 128, N = 128 product [dS^T ; P^T] [Q | dO] per 16 queries (8 MMAs per step, lane = key
+//   row layout) instead of two M = 64, N = 64 products (16 half-rate MMAs in the scattered M = 64 lane layout): rows
+//   0-63 x columns 0-63 are dK, rows 64-127 x columns 64-127 are dV, the two off-diagonal blocks are discarded — the
+//   tensor pipe has the room (26 % busy), the single MMA-issuing thread and the read-out warps do not.  Both operands
+//   are MN-major with the second 64-wide block at a fixed distance (P after dS, dO after Q in shared memory).
+//   TMEM (512 columns): S0 | dP0 | S1 | dP1 | dQ_0 | dQ_1 (64 each) | dK/dV product (128).
 // Warps: 0-7 / 8-15 two compute groups — group g owns the steps of parity g, so one group's exp / dS phase overlaps the
 // other group's MMAs (the two-CTAs-per-SM overlap of the key-block kernel, inside one CTA); 16-19 read out dK / dV /
 // dQ (one per TMEM lane quadrant) while the compute groups continue; 20 issues the MMAs; 21 drives TMA.  The next
@@ -924,14 +929,63 @@ struct AttnBwdShortSmem {
   static constexpr int kV = 32768;
   static constexpr int kQ = 65536;                   // 3 slots x (128 x 128 B)
   static constexpr int kDO = kQ + 3 * 16384;
-  static constexpr int kP = kDO + 3 * 16384;         // 2 x (128 x 128 B)
-  static constexpr int kDS = kP + 2 * 16384;
-  static constexpr int kBar = kDS + 2 * 16384;
+  static constexpr int kDS = kDO + 3 * 16384;        // 2 x (128 x 128 B)
+  static constexpr int kP = kDS + 2 * 16384;         // after dS and Q before dO: see the stacked dK / dV product below
+  static constexpr int kBar = kP + 2 * 16384;
   static constexpr int kTotal = kBar + 512 + 1024;
 };
 static_assert(AttnBwdShortSmem::kTotal <= 227 * 1024, "attention backward (short): shared memory budget");
 constexpr int kBwdShortThreads = 22 * 32;
 
+// P / dS of 16 consecutive keys of one query row.  kDrop / kTail are compile-time so that the common paths carry neither
+// the dropout hash nor the per-key bound checks of the sequence's last key block (ncu r02: 23 instructions per score in
+// the first version; the exponent, one FMA for the scaled score, one for dP - delta, one product and half a bf16 pack
+// are what the mathematics needs).  dS is produced WITHOUT the softmax scale: the read-out warps apply it to dQ and dK.
+template <bool kDrop, bool kTail>
+__device__ __forceinline__ void bwd_chunk16(const uint32_t (&sv)[16], const uint32_t (&dv)[16], float sl2, float l2, float dl,
+                                            float dscale, uint32_t thresh, uint32_t dseed, uint32_t elem0, int nvalid,
+                                            uint32_t (&pk)[8], uint32_t (&dsk)[8]) {
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    bool keep[2] = {true, true};
+    if (kDrop) drop_keep2(elem0 + (uint32_t)k, dseed, thresh, keep[0], keep[1]);
+    float pdv[2], dsv[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float pv = ex2_approx(fmaf(__uint_as_float(sv[k + t]), sl2, -l2));
+      if (kTail) pv = (k + t < nvalid) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
+      if (kDrop) {
+        // forward used P_drop = m * P / (1 - p): dV needs P_drop, and dP arrives w.r.t. P_drop
+        const float mk = keep[t] ? dscale : 0.0f;
+        pdv[t] = pv * mk;
+        dsv[t] = pv * fmaf(__uint_as_float(dv[k + t]), mk, -dl);
+      } else {
+        pdv[t] = pv;
+        dsv[t] = pv * (__uint_as_float(dv[k + t]) - dl);
+      }
+    }
+    pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
+    dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
+  }
+}
+
+// -DVS_ATTN_TRACE: CTA 0 records (event, global step, clock) triples of its control flow — the timeline tool used to
+// find where the step period of this kernel goes (tools/attn_trace.py).  Not compiled into the shipped library.
+#ifdef VS_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[1 << 16];
+__device__ unsigned int g_attn_trace_n;
+__device__ __forceinline__ void attn_trace(int ev, unsigned step) {
+  if (blockIdx.x != 0) return;
+  const unsigned i = atomicAdd(&g_attn_trace_n, 1u);
+  if (i < (1u << 16)) g_attn_trace[i] = ((unsigned long long)ev << 56) | ((unsigned long long)(step & 0xFFFFu) << 40) |
+                                        ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+}
+#define ATTN_TRACE(ev, step) attn_trace(ev, step)
+#else
+#define ATTN_TRACE(ev, step)
+#endif
+
+template <bool kDrop>
 __global__ void __launch_bounds__(kBwdShortThreads, 1)
 attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_constant__ CUtensorMap tmap_q,
                       const __grid_constant__ CUtensorMap tmap_do, const float* __restrict__ lse,
@@ -1028,14 +1082,16 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
     const uint32_t aP = smem_u32(smem + AttnBwdShortSmem::kP), aDS = smem_u32(smem + AttnBwdShortSmem::kDS);
     const uint32_t kQ_k = umma_desc_lo(aQ, 16), kK_k = umma_desc_lo(aK, 16), kDO_k = umma_desc_lo(aDO, 16),
                    kV_k = umma_desc_lo(aV, 16), kDS_k = umma_desc_lo(aDS, 16);                  // K-major
-    const uint32_t kK_mn = umma_desc_lo(aK, 16384), kDO_mn = umma_desc_lo(aDO, 16384), kQ_mn = umma_desc_lo(aQ, 16384),
-                   kP_mn = umma_desc_lo(aP, 16384), kDS_mn = umma_desc_lo(aDS, 16384);          // MN-major
+    const uint32_t kK_mn = umma_desc_lo(aK, 16384);                                             // MN-major
+    // stacked operands of the dK / dV product: 128 rows = 64 of dS^T then 64 of P^T; 128 columns = 64 of Q then 64 of dO
+    const uint32_t kDSP_mn = umma_desc_lo(aDS, AttnBwdShortSmem::kP - AttnBwdShortSmem::kDS);
+    const uint32_t kQDO_mn = umma_desc_lo(aQ, AttnBwdShortSmem::kDO - AttnBwdShortSmem::kQ);
     constexpr uint32_t kSlot = 16384 >> 4, kBlk = 8192 >> 4, kStep16 = 2048 >> 4;   // Q / dO slot (= P / dS buffer), K / V block, 16 rows
-    const uint32_t id_dq = umma_idesc_bf16(kBQ, kDH, 0, 1), id_dkv = umma_idesc_bf16(kKB, kDH, 1, 1);
+    const uint32_t id_dq = umma_idesc_bf16(kBQ, kDH, 0, 1), id_dkv = umma_idesc_bf16(128, 128, 1, 1);
     const uint32_t id_s_full = umma_idesc_bf16(kBQ, kKB, 0, 0);
     const int ncols_tail = (N - (nkb - 1) * kKB + 15) & ~15;
     const uint32_t id_s_tail = umma_idesc_bf16(kBQ, ncols_tail, 0, 0);
-    const uint32_t tm_dq = tmem_base + 256, tm_dk = tmem_base + 384, tm_dv = tmem_base + 448;
+    const uint32_t tm_dq = tmem_base + 256, tm_dkv = tmem_base + 384;
     int it = 0;
     uint32_t g = 0;   // steps issued so far by this CTA: buffer = g & 1, use count of the buffer = g >> 1
     auto issue_sdp = [&](int it_, int s, uint32_t gs) {   // S / dP of step s of this CTA's item number it_
@@ -1089,12 +1145,13 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
         const int sl = qslot(it, qt);
         const int nk16 = (kb == nkb - 1 ? ncols_tail : kKB) >> 4;
         mbar_wait(&pfull[bsel], (gs >> 1) & 1u);
+        if (lane == 0) ATTN_TRACE(1, gs);    // MMA warp: P / dS of step gs received
         while (ahead.w < total && g_ahead <= gs + 2 && operands_ready(ahead)) issue_ahead();
+        if (lane == 0) ATTN_TRACE(2, gs);    // MMA warp: look-ahead S / dP issued
         if (s == 0 && it > 0) mbar_wait(dqfree, (uint32_t)(it - 1) & 1u);   // the previous item's dQ has been read out
         tc_fence_after();
         const uint32_t ds_k = kDS_k + bsel * kSlot, k_mn = kK_mn + kb * kBlk;
-        const uint32_t p_mn = kP_mn + bsel * kSlot, ds_mn = kDS_mn + bsel * kSlot;
-        const uint32_t do_mn = kDO_mn + sl * kSlot, q_mn = kQ_mn + sl * kSlot;
+        const uint32_t dsp_mn = kDSP_mn + bsel * kSlot, qdo_mn = kQDO_mn + sl * kSlot;
         if (elect_one()) {
           // dQ_qt (+)= dS K_kb : A = dS K-major (M = 128 queries, K = keys), B = K_kb MN-major (N = 64)
           for (int kk = 0; kk < nk16; ++kk)
@@ -1108,14 +1165,12 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
             tc_fence_after();
           }
         }
+        if (lane == 0) ATTN_TRACE(3, gs);    // MMA warp: dQ issued, dK / dV accumulator free
         if (elect_one()) {
-          // dV_kb (+)= P^T dO_qt, dK_kb (+)= dS^T Q_qt : A read MN-major (M = 64 keys, K = 128 queries), B MN-major
+          // [dK | . ; . | dV]_kb (+)= [dS^T ; P^T] [Q_qt | dO_qt] : both operands MN-major, reduction over the 128 queries
 #pragma unroll
           for (int kk = 0; kk < kBQ / 16; ++kk)
-            umma_bf16_lo(tm_dv, p_mn + kk * kStep16, do_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
-#pragma unroll
-          for (int kk = 0; kk < kBQ / 16; ++kk)
-            umma_bf16_lo(tm_dk, ds_mn + kk * kStep16, q_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
+            umma_bf16_lo(tm_dkv, dsp_mn + kk * kStep16, qdo_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
           umma_commit(&pfree[bsel]);
           if (j == nq - 1) {
             umma_commit(kvfull);
@@ -1125,6 +1180,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
           if (s == nsteps - 1) umma_commit(dqfull);
         }
         __syncwarp();
+        if (lane == 0) ATTN_TRACE(4, gs);    // MMA warp: gradient MMAs of step gs issued
         if (ahead.w < total && g_ahead == gs + 1) issue_ahead();   // the next step must be under way: wait for its loads
       }
       g += (uint32_t)nsteps;
@@ -1133,60 +1189,79 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
     // ---------------------------------------------------------------- read-out warps (one per TMEM lane quadrant)
     const int quad = warp & 3;
     const uint32_t lane_off = uint32_t(quad * 32) << 16;
-    const uint32_t tm_dq = tmem_base + 256, tm_dk = tmem_base + 384, tm_dv = tmem_base + 448;
+    const uint32_t tm_dq = tmem_base + 256, tm_dkv = tmem_base + 384;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int h = w % H, b = w / H;
       for (int kb = 0; kb < nkb; ++kb) {
         const int ckv = it * nkb + kb;
         mbar_wait(kvfull, (uint32_t)ckv & 1u);
+        if (warp == 16 && lane == 0) ATTN_TRACE(5, ckv);   // read-out: dK / dV of key block ckv complete
         tc_fence_after();
-        // M = 64 accumulators: lanes 0-15 of quadrant `quad` hold keys 16 * quad .. + 15 of the block
-        const int kv = kb * kKB + quad * 16 + lane;
-        const bool kv_ok = lane < 16 && kv < N;
+        // lanes 0-63 (quadrants 0, 1): dK rows in columns 0-63; lanes 64-127: dV rows in columns 64-127
+        const int kv = kb * kKB + (quad & 1) * 32 + lane;
+        const bool is_dv = quad >= 2;
+        __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (is_dv ? 2 * D : D) + h * kDH;
+        const uint32_t src = tm_dkv + lane_off + (is_dv ? 64u : 0u);
 #pragma unroll
-        for (int which = 0; which < 2; ++which) {
-          const uint32_t src = which == 0 ? tm_dk : tm_dv;
-          __nv_bfloat16* dst = dqkv + ((size_t)b * N + kv) * (3 * D) + (which == 0 ? D : 2 * D) + h * kDH;
+        for (int c2 = 0; c2 < 2; ++c2) {   // 32 columns per round trip (64 at once spill: the kernel runs at 88 registers)
+          uint32_t va[16], vb[16];
+          tmem_ld16(src + c2 * 32, va);
+          tmem_ld16(src + c2 * 32 + 16, vb);
+          tmem_ld_wait();
+          if (c2 == 1) {   // the accumulator has been read: the next key block's MMAs may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(kvfree);
+            if (warp == 16 && lane == 0) ATTN_TRACE(6, ckv);   // read-out: accumulator released
+          }
+          if (kv < N) {
+            const float f = is_dv ? 1.0f : scale;   // dS was formed without the softmax scale
+            u32x8 o;
 #pragma unroll
-          for (int c = 0; c < kDH; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(src + lane_off + c, v);
-            tmem_ld_wait();
-            if (kv_ok) {
-              u32x8 o;
+            for (int jj = 0; jj < 8; ++jj)
+              o.v[jj] = pack_bf16(__uint_as_float(va[2 * jj]) * f, __uint_as_float(va[2 * jj + 1]) * f);
+            st_global_256(dst + c2 * 32, o);
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) o.v[jj] = pack_bf16(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
-              st_global_256(dst + c, o);
-            }
+            for (int jj = 0; jj < 8; ++jj)
+              o.v[jj] = pack_bf16(__uint_as_float(vb[2 * jj]) * f, __uint_as_float(vb[2 * jj + 1]) * f);
+            st_global_256(dst + c2 * 32 + 16, o);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(kvfree);
       }
       mbar_wait(dqfull, (uint32_t)it & 1u);
       tc_fence_after();
       for (int qt = 0; qt < nq; ++qt) {
         const int q = qt * kBQ + quad * 32 + lane;
-        if (qt * kBQ + quad * 32 >= N) break;   // warp-uniform: no live query row in this quadrant
+        const bool live = qt * kBQ + quad * 32 < N;   // warp-uniform: a live query row in this quadrant
         __nv_bfloat16* dst = dqkv + ((size_t)b * N + q) * (3 * D) + h * kDH;
+        const uint32_t src = tm_dq + qt * 64 + lane_off;
 #pragma unroll
-        for (int c = 0; c < kDH; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(tm_dq + qt * 64 + lane_off + c, v);
-          tmem_ld_wait();
-          if (q < N) {
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t va[16], vb[16];
+          if (live) {
+            tmem_ld16(src + c2 * 32, va);
+            tmem_ld16(src + c2 * 32 + 16, vb);
+            tmem_ld_wait();
+          }
+          if (qt == nq - 1 && c2 == 1) {   // dQ has been read: the next item's dQ MMAs may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dqfree);
+          }
+          if (live && q < N) {
             u32x8 o;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) o.v[jj] = pack_bf16(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
-            st_global_256(dst + c, o);
+            for (int jj = 0; jj < 8; ++jj)
+              o.v[jj] = pack_bf16(__uint_as_float(va[2 * jj]) * scale, __uint_as_float(va[2 * jj + 1]) * scale);
+            st_global_256(dst + c2 * 32, o);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              o.v[jj] = pack_bf16(__uint_as_float(vb[2 * jj]) * scale, __uint_as_float(vb[2 * jj + 1]) * scale);
+            st_global_256(dst + c2 * 32 + 16, o);
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dqfree);
     }
   } else {
     // ---------------------------------------------------------------- compute warps: group = step parity
@@ -1197,22 +1272,30 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
     uint8_t* sDS = smem + AttnBwdShortSmem::kDS + grp * 16384;
     const uint32_t tm_s = tmem_base + (uint32_t)grp * 128u, tm_dp = tm_s + 64u;
     const float sl2 = scale * kLog2e;
-    const uint32_t dseed0 = drop.thresh != 0u ? drop_seed(drop) : 0u;
-    const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
+    const uint32_t dseed0 = kDrop ? drop_seed(drop) : 0u;
+    const float dscale = kDrop ? drop.scale : 1.0f;
     uint32_t g = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      // per-row statistics of both query tiles (rows beyond the sequence: lse = +inf -> exp2(s - lse) = 0)
-      float lse2[2] = {INFINITY, INFINITY}, dlt[2] = {0.0f, 0.0f};
+    // per-row statistics of both query tiles (rows beyond the sequence: lse = +inf -> exp2(s - lse) = 0); the next
+    // item's are requested while the current item is processed
+    float lse2_n[2], dlt_n[2];
+    auto fetch_stats = [&](int w_) {
 #pragma unroll
       for (int qt = 0; qt < 2; ++qt) {
+        lse2_n[qt] = INFINITY;
+        dlt_n[qt] = 0.0f;
         const int q = qt * kBQ + r;
-        if (qt < nq && q < N) {
-          const size_t o = (size_t)w * N + q;   // (b * H + h) * N + q
-          lse2[qt] = lse[o] * kLog2e;
-          dlt[qt] = delta[o];
+        if (w_ < total && qt < nq && q < N) {
+          const size_t o = (size_t)w_ * N + q;   // (b * H + h) * N + q
+          lse2_n[qt] = lse[o];
+          dlt_n[qt] = delta[o];
         }
       }
-      const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)w, dseed0) : 0u;   // per (batch, head)
+    };
+    fetch_stats(blockIdx.x);
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const float lse2[2] = {lse2_n[0] * kLog2e, lse2_n[1] * kLog2e}, dlt[2] = {dlt_n[0], dlt_n[1]};
+      fetch_stats(w + gridDim.x);
+      const uint32_t dseed = kDrop ? drop_hash((uint32_t)w, dseed0) : 0u;   // per (batch, head)
       for (int s = 0; s < nsteps; ++s) {
         const uint32_t gs = g + s;
         if ((int)(gs & 1u) != grp) continue;
@@ -1227,8 +1310,9 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
         const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
         const float l2 = qt == 0 ? lse2[0] : lse2[1], dl = qt == 0 ? dlt[0] : dlt[1];
         const bool warp_dead = qt * kBQ + quad * 32 >= N;   // no live query row in this warp: P = dS = 0
+        if ((warp & 7) == 0 && lane == 0) ATTN_TRACE(7, gs);    // compute: waiting for S / dP of step gs
         mbar_wait(&sfull[grp], u & 1u);
-        if (u > 0) mbar_wait(&pfree[grp], (u - 1) & 1u);   // the MMAs of this buffer's previous step have read P / dS
+        if ((warp & 7) == 0 && lane == 0) ATTN_TRACE(8, gs);    // compute: S / dP received
         tc_fence_after();
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -1239,28 +1323,19 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
             tmem_ld16(tm_s + lane_off + c, sv);
             tmem_ld16(tm_dp + lane_off + c, dv);
             tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-              bool keep[2] = {true, true};
-              if (drop.thresh != 0u)
-                drop_keep2(2u * (drow + (uint32_t)((kv0 + c + k) >> 1)), dseed, drop.thresh, keep[0], keep[1]);
-              float pdv[2], dsv[2];
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                float pv = ex2_approx(__uint_as_float(sv[k + t]) * sl2 - l2);
-                if (tail_block) pv = (c + k + t < nvalid_kv) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
-                // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
-                const float mk = keep[t] ? dscale : 0.0f;
-                pdv[t] = pv * mk;
-                dsv[t] = (pv * scale) * (__uint_as_float(dv[k + t]) * mk - dl);
-              }
-              pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
-              dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
-            }
+            const uint32_t elem0 = 2u * (drow + (uint32_t)((kv0 + c) >> 1));
+            if (tail_block)
+              bwd_chunk16<kDrop, true>(sv, dv, sl2, l2, dl, dscale, drop.thresh, dseed, elem0, nvalid_kv - c, pk, dsk);
+            else
+              bwd_chunk16<kDrop, false>(sv, dv, sl2, l2, dl, dscale, drop.thresh, dseed, elem0, 16, pk, dsk);
           } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) { pk[k] = 0u; dsk[k] = 0u; }
           }
+          // the MMAs of this buffer's previous step must have finished reading P / dS — waited for as late as possible
+          if (cc == 0 && (warp & 7) == 0 && lane == 0) ATTN_TRACE(9, gs);   // compute: first chunk done, waiting for the P / dS buffer
+          if (cc == 0 && u > 0) mbar_wait(&pfree[grp], (u - 1) & 1u);
+          if (cc == 0 && (warp & 7) == 0 && lane == 0) ATTN_TRACE(10, gs);
           const uint32_t slot = uint32_t(c >> 3);     // 16-byte slot inside the 128-byte (64-key) row
           *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(sP + sw128_offset(r, slot + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -1270,6 +1345,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&pfull[grp]);
+        if ((warp & 7) == 0 && lane == 0) ATTN_TRACE(11, gs);   // compute: P / dS handed over
       }
       g += (uint32_t)nsteps;
     }
@@ -1403,14 +1479,19 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
     // short sequences: one persistent CTA per SM owns whole (batch, head) items; dQ leaves as bf16 in dqkv
     static bool attr_s = false;
     if (!attr_s) {
-      VS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      VS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnBwdShortSmem::kTotal));
+      VS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          AttnBwdShortSmem::kTotal));
       attr_s = true;
     }
     const long long bh = (long long)B * H;
     const int nsm_s = sm_count();
     const unsigned grid_s = (unsigned)(bh < nsm_s ? bh : nsm_s);
-    launch_k(attn_bwd_short_kernel, dim3(grid_s), dim3(kBwdShortThreads), (size_t)(AttnBwdShortSmem::kTotal), st, tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, B, N, H, scale, dc);
+    if (dc.thresh != 0u)
+      launch_k(attn_bwd_short_kernel<true>, dim3(grid_s), dim3(kBwdShortThreads), (size_t)(AttnBwdShortSmem::kTotal), st, tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, B, N, H, scale, dc);
+    else
+      launch_k(attn_bwd_short_kernel<false>, dim3(grid_s), dim3(kBwdShortThreads), (size_t)(AttnBwdShortSmem::kTotal), st, tkv, tq, tdo, lse, delta, (__nv_bfloat16*)dqkv, B, N, H, scale, dc);
     VS_CHECK_LAUNCH();
     return 0;
   }
@@ -1429,3 +1510,17 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   VS_CHECK_LAUNCH();
   return 0;
 }
+
+#ifdef VS_ATTN_TRACE
+extern "C" int vs_debug_attn_trace(unsigned long long* host, int cap) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_attn_trace_n, sizeof(n));
+  if ((int)n > cap) n = cap;
+  if (n > (1u << 16)) n = 1u << 16;
+  cudaMemcpyFromSymbol(host, g_attn_trace, n * sizeof(unsigned long long));
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_attn_trace_n, &zero, sizeof(zero));
+  return (int)n;
+}
+#endif
