@@ -919,9 +919,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
 //   tensor pipe has the room (26 % busy), the single MMA-issuing thread and the read-out warps do not.  Both operands
 //   are MN-major with the second 64-wide block at a fixed distance (P after dS, dO after Q in shared memory).
 //   TMEM (512 columns): S0 | dP0 | S1 | dP1 | dQ_0 | dQ_1 (64 each) | dK/dV product (128).
-// Warps: 0-7 / 8-15 two compute groups — group g owns the steps of parity g, so one group's exp / dS phase overlaps the
+// Warps (24; 21 and 22 idle): 0-7 / 8-15 two compute groups — group g owns the steps of parity g, so one group's exp / dS phase overlaps the
 // other group's MMAs (the two-CTAs-per-SM overlap of the key-block kernel, inside one CTA); 16-19 read out dK / dV /
-// dQ (one per TMEM lane quadrant) while the compute groups continue; 20 issues the MMAs; 21 drives TMA.  The next
+// dQ (one per TMEM lane quadrant) while the compute groups continue; 20 drives TMA; 23 issues the MMAs (on the
+// sub-partition whose compute warps have the least to do: the r02 timeline showed the issuing warp, not the tensor pipe,
+// pacing the steps — ~2700 cycles to issue one step's 20 MMAs while sharing a scheduler with four busy compute warps).  The next
 // item's K / V blocks and query tiles are loaded as soon as the current item's last MMA on that buffer has retired
 // (per-buffer mbarriers; a third Q / dO slot holds the next item's first query tile).
 struct AttnBwdShortSmem {
@@ -935,7 +937,8 @@ struct AttnBwdShortSmem {
   static constexpr int kTotal = kBar + 512 + 1024;
 };
 static_assert(AttnBwdShortSmem::kTotal <= 227 * 1024, "attention backward (short): shared memory budget");
-constexpr int kBwdShortThreads = 22 * 32;
+constexpr int kBwdShortThreads = 24 * 32;
+constexpr int kBwdShortMmaWarp = 23;   // sub-partition 3: its compute warps own the (often empty) last row quadrant
 
 // P / dS of 16 consecutive keys of one query row.  kDrop / kTail are compile-time so that the common paths carry neither
 // the dropout hash nor the per-key bound checks of the sequence's last key block (ncu r02: 23 instructions per score in
@@ -972,15 +975,17 @@ __device__ __forceinline__ void bwd_chunk16(const uint32_t (&sv)[16], const uint
 // -DVS_ATTN_TRACE: CTA 0 records (event, global step, clock) triples of its control flow — the timeline tool used to
 // find where the step period of this kernel goes (tools/attn_trace.py).  Not compiled into the shipped library.
 #ifdef VS_ATTN_TRACE
-__device__ unsigned long long g_attn_trace[1 << 16];
-__device__ unsigned int g_attn_trace_n;
-__device__ __forceinline__ void attn_trace(int ev, unsigned step) {
-  if (blockIdx.x != 0) return;
-  const unsigned i = atomicAdd(&g_attn_trace_n, 1u);
-  if (i < (1u << 16)) g_attn_trace[i] = ((unsigned long long)ev << 56) | ((unsigned long long)(step & 0xFFFFu) << 40) |
-                                        ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+// four tracing threads (MMA warp, read-out warp 16, compute warps 0 and 8; lane 0 each), each with a private slice and a
+// private counter: a record costs one clock read and one fire-and-forget store
+__device__ unsigned long long g_attn_trace[4 << 13];
+__device__ __forceinline__ void attn_trace(int ev, unsigned step, unsigned& n) {
+  if (blockIdx.x != 0 || n >= (1u << 13)) return;
+  const int warp = threadIdx.x >> 5;
+  const int role = warp >= kBwdShortMmaWarp - 1 ? 0 : (warp >= 16 ? 1 : (warp < 8 ? 2 : 3));
+  g_attn_trace[role * (1 << 13) + n++] = ((unsigned long long)ev << 56) | ((unsigned long long)(step & 0xFFFFu) << 40) |
+                                         ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
 }
-#define ATTN_TRACE(ev, step) attn_trace(ev, step)
+#define ATTN_TRACE(ev, step) attn_trace(ev, step, trace_n)
 #else
 #define ATTN_TRACE(ev, step)
 #endif
@@ -995,26 +1000,28 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdShortSmem::kBar);
   uint64_t* kfull = bars + 0;     // [4] K / V block landed
-  uint64_t* kfree = bars + 4;     // [4] last MMA reading the block retired
+  uint64_t* kfree = bars + 4;     // [4] last MMA of the block retired: K / V block free, dK / dV of the block complete
   uint64_t* qfull = bars + 8;     // [3] Q / dO slot landed
   uint64_t* qfree = bars + 11;    // [3]
   uint64_t* sfull = bars + 14;    // [2] S / dP of a step complete
   uint64_t* pfull = bars + 16;    // [2] P / dS of a step in shared memory (256 arrivals); S / dP consumed
   uint64_t* pfree = bars + 18;    // [2] the MMAs reading P / dS retired
-  uint64_t* kvfull = bars + 20;   // dK / dV of a key block complete
-  uint64_t* kvfree = bars + 21;   // ... and read out (4 arrivals)
+  uint64_t* kvfree = bars + 21;   // dK / dV of a key block (complete with kfree[kb]) have been read out (4 arrivals)
   uint64_t* dqfull = bars + 22;   // dQ of the item complete
   uint64_t* dqfree = bars + 23;   // ... and read out (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef VS_ATTN_TRACE
+  unsigned trace_n = 0;
+#endif
   const int D = H * kDH;
   const int nq = (N + kBQ - 1) / kBQ;      // 1 or 2
   const int nkb = (N + kKB - 1) / kKB;     // 1 .. 4
   const int nsteps = nq * nkb;
   const int total = B * H;
 
-  if (warp == 20) {
+  if (warp == kBwdShortMmaWarp) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_kv);
       tma_prefetch_desc(&tmap_q);
@@ -1022,7 +1029,6 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
       for (int i = 0; i < 4; ++i) { mbar_init(&kfull[i], 1); mbar_init(&kfree[i], 1); }
       for (int i = 0; i < 3; ++i) { mbar_init(&qfull[i], 1); mbar_init(&qfree[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pfull[i], 256); mbar_init(&pfree[i], 1); }
-      mbar_init(kvfull, 1);
       mbar_init(kvfree, 4);
       mbar_init(dqfull, 1);
       mbar_init(dqfree, 4);
@@ -1050,7 +1056,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
   auto qslot = [&](int it, int qt) { return qt == 1 ? 1 : ((it & 1) ? 2 : 0); };
   auto quse = [&](int it, int sl) { return sl == 1 ? it : (it >> 1); };   // how often the slot was used before item it
 
-  if (warp == 21) {
+  if (warp == 20) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int it = 0;
@@ -1074,117 +1080,114 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
         for (int kb = 1; kb < nkb; ++kb) load_kv(kb);
       }
     }
-  } else if (warp == 20) {
-    // ---------------------------------------------------------------- MMA issuer (converged warp, elected lane)
+  } else if (warp == kBwdShortMmaWarp || warp == kBwdShortMmaWarp - 1) {
+    // ---------------------------------------------------------------- MMA issuers (converged warps, elected lane)
+    // Two warps on the two quietest sub-partitions share the issue work — r02 timeline: ONE warp needed ~3000 cycles per
+    // step for 20 MMAs whose dispatch floor is ~900 (every mbarrier probe / commit of that warp took ~150 cycles behind
+    // the compute warps' shared-memory traffic) and paced the whole kernel.
+    //   warp 23: S = Q K^T and dP = dO V^T of every step, as soon as the step's TMEM buffer has been handed back
+    //            (pfull of the step two before) and its operands have landed;
+    //   warp 22: the gradient MMAs (dQ, stacked dK / dV) of every step once its P / dS are in shared memory, and
+    //            every commit that releases shared memory — a gradient MMA of step gs is issued after pfull(gs), i.e.
+    //            after the compute warps have read S(gs), so the S / dP MMAs reading the same K / V block or query
+    //            slot have retired by then and this warp's commit covers them.
     // one descriptor low word per operand and layout; offsets are added in 16-byte units (umma_desc_lo)
     const uint32_t aK = smem_u32(smem + AttnBwdShortSmem::kK), aV = smem_u32(smem + AttnBwdShortSmem::kV);
     const uint32_t aQ = smem_u32(smem + AttnBwdShortSmem::kQ), aDO = smem_u32(smem + AttnBwdShortSmem::kDO);
-    const uint32_t aP = smem_u32(smem + AttnBwdShortSmem::kP), aDS = smem_u32(smem + AttnBwdShortSmem::kDS);
-    const uint32_t kQ_k = umma_desc_lo(aQ, 16), kK_k = umma_desc_lo(aK, 16), kDO_k = umma_desc_lo(aDO, 16),
-                   kV_k = umma_desc_lo(aV, 16), kDS_k = umma_desc_lo(aDS, 16);                  // K-major
-    const uint32_t kK_mn = umma_desc_lo(aK, 16384);                                             // MN-major
-    // stacked operands of the dK / dV product: 128 rows = 64 of dS^T then 64 of P^T; 128 columns = 64 of Q then 64 of dO
-    const uint32_t kDSP_mn = umma_desc_lo(aDS, AttnBwdShortSmem::kP - AttnBwdShortSmem::kDS);
-    const uint32_t kQDO_mn = umma_desc_lo(aQ, AttnBwdShortSmem::kDO - AttnBwdShortSmem::kQ);
+    const uint32_t aDS = smem_u32(smem + AttnBwdShortSmem::kDS);
     constexpr uint32_t kSlot = 16384 >> 4, kBlk = 8192 >> 4, kStep16 = 2048 >> 4;   // Q / dO slot (= P / dS buffer), K / V block, 16 rows
-    const uint32_t id_dq = umma_idesc_bf16(kBQ, kDH, 0, 1), id_dkv = umma_idesc_bf16(128, 128, 1, 1);
-    const uint32_t id_s_full = umma_idesc_bf16(kBQ, kKB, 0, 0);
     const int ncols_tail = (N - (nkb - 1) * kKB + 15) & ~15;
-    const uint32_t id_s_tail = umma_idesc_bf16(kBQ, ncols_tail, 0, 0);
-    const uint32_t tm_dq = tmem_base + 256, tm_dkv = tmem_base + 384;
-    int it = 0;
-    uint32_t g = 0;   // steps issued so far by this CTA: buffer = g & 1, use count of the buffer = g >> 1
-    auto issue_sdp = [&](int it_, int s, uint32_t gs) {   // S / dP of step s of this CTA's item number it_
-      int kb, j, qt;
-      decode(s, kb, j, qt);
-      const int sl = qslot(it_, qt);
-      mbar_wait(&kfull[kb], (uint32_t)it_ & 1u);
-      mbar_wait(&qfull[sl], (uint32_t)quse(it_, sl) & 1u);
-      tc_fence_after();
-      const uint32_t idesc = kb == nkb - 1 ? id_s_tail : id_s_full;
-      const uint32_t qd = kQ_k + sl * kSlot, kd = kK_k + kb * kBlk, od = kDO_k + sl * kSlot, vd = kV_k + kb * kBlk;
-      const uint32_t tm_s = tmem_base + (gs & 1u) * 128u, tm_dp = tm_s + 64u;
-      if (elect_one()) {
+    if (warp == kBwdShortMmaWarp) {
+      const uint32_t kQ_k = umma_desc_lo(aQ, 16), kK_k = umma_desc_lo(aK, 16), kDO_k = umma_desc_lo(aDO, 16),
+                     kV_k = umma_desc_lo(aV, 16);                                               // K-major
+      const uint32_t id_s_full = umma_idesc_bf16(kBQ, kKB, 0, 0), id_s_tail = umma_idesc_bf16(kBQ, ncols_tail, 0, 0);
+      int it = 0;
+      uint32_t g = 0;   // steps issued so far by this CTA: buffer = g & 1, use count of the buffer = g >> 1
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        for (int s = 0; s < nsteps; ++s) {
+          int kb, j, qt;
+          decode(s, kb, j, qt);
+          const uint32_t gs = g + s, bsel = gs & 1u;
+          const int sl = qslot(it, qt);
+          if (lane == 0) ATTN_TRACE(12, gs);
+          // operands: probed once per item and buffer (first use)
+          if (j == 0) mbar_wait(&kfull[kb], (uint32_t)it & 1u);
+          if (kb == 0) mbar_wait(&qfull[sl], (uint32_t)quse(it, sl) & 1u);
+          // the step two before has handed over its P / dS, i.e. has consumed this S / dP buffer
+          if (gs >= 2) mbar_wait(&pfull[bsel], ((gs - 2) >> 1) & 1u);
+          tc_fence_after();
+          if (lane == 0) ATTN_TRACE(13, gs);
+          const uint32_t idesc = kb == nkb - 1 ? id_s_tail : id_s_full;
+          const uint32_t qd = kQ_k + sl * kSlot, kd = kK_k + kb * kBlk, od = kDO_k + sl * kSlot, vd = kV_k + kb * kBlk;
+          const uint32_t tm_s = tmem_base + bsel * 128u, tm_dp = tm_s + 64u;
+          if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kDH / 16; ++k) umma_bf16_lo(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
+            for (int k = 0; k < kDH / 16; ++k) umma_bf16_lo(tm_s, qd + 2 * k, kd + 2 * k, idesc, k > 0);
 #pragma unroll
-        for (int k = 0; k < kDH / 16; ++k) umma_bf16_lo(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
-        umma_commit(&sfull[gs & 1u]);
-      }
-      __syncwarp();
-    };
-    // S / dP run up to two steps ahead of the gradient MMAs (one per TMEM buffer), across item boundaries too: the
-    // buffer of step gs + 2 is the one step gs has just handed back with its P / dS.  A step further ahead than the
-    // very next one is only issued if its operands have already landed (its K block / query slot may still be
-    // waiting for a commit that follows in program order: blocking there would deadlock); the very next step only
-    // depends on steps that have been committed and may be waited for.
-    struct Pos { int it, s, w; };
-    auto next_pos = [&](Pos p) {
-      if (p.s + 1 < nsteps) return Pos{p.it, p.s + 1, p.w};
-      return Pos{p.it + 1, 0, p.w + (int)gridDim.x};
-    };
-    auto operands_ready = [&](const Pos& p) {
-      int kb, j, qt;
-      decode(p.s, kb, j, qt);
-      const int sl = qslot(p.it, qt);
-      return mbar_test_wait(&kfull[kb], (uint32_t)p.it & 1u) && mbar_test_wait(&qfull[sl], (uint32_t)quse(p.it, sl) & 1u);
-    };
-    Pos ahead{0, 0, (int)blockIdx.x};   // next step whose S / dP have not been issued yet
-    uint32_t g_ahead = 0;
-    auto issue_ahead = [&]() {
-      issue_sdp(ahead.it, ahead.s, g_ahead++);
-      ahead = next_pos(ahead);
-    };
-    if (ahead.w < total) issue_ahead();
-    if (ahead.w < total && operands_ready(ahead)) issue_ahead();
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      for (int s = 0; s < nsteps; ++s) {
-        int kb, j, qt;
-        decode(s, kb, j, qt);
-        const uint32_t gs = g + s, bsel = gs & 1u;
-        const int sl = qslot(it, qt);
-        const int nk16 = (kb == nkb - 1 ? ncols_tail : kKB) >> 4;
-        mbar_wait(&pfull[bsel], (gs >> 1) & 1u);
-        if (lane == 0) ATTN_TRACE(1, gs);    // MMA warp: P / dS of step gs received
-        while (ahead.w < total && g_ahead <= gs + 2 && operands_ready(ahead)) issue_ahead();
-        if (lane == 0) ATTN_TRACE(2, gs);    // MMA warp: look-ahead S / dP issued
-        if (s == 0 && it > 0) mbar_wait(dqfree, (uint32_t)(it - 1) & 1u);   // the previous item's dQ has been read out
-        tc_fence_after();
-        const uint32_t ds_k = kDS_k + bsel * kSlot, k_mn = kK_mn + kb * kBlk;
-        const uint32_t dsp_mn = kDSP_mn + bsel * kSlot, qdo_mn = kQDO_mn + sl * kSlot;
-        if (elect_one()) {
-          // dQ_qt (+)= dS K_kb : A = dS K-major (M = 128 queries, K = keys), B = K_kb MN-major (N = 64)
-          for (int kk = 0; kk < nk16; ++kk)
-            umma_bf16_lo(tm_dq + qt * 64, ds_k + 2 * kk, k_mn + kk * kStep16, id_dq, (kb > 0 || kk > 0));
-        }
-        __syncwarp();
-        if (j == 0) {
-          const int ckv = it * nkb + kb;   // key blocks completed so far
-          if (ckv > 0) {
-            mbar_wait(kvfree, (uint32_t)(ckv - 1) & 1u);   // dK / dV of the previous key block have been read out
-            tc_fence_after();
+            for (int k = 0; k < kDH / 16; ++k) umma_bf16_lo(tm_dp, od + 2 * k, vd + 2 * k, idesc, k > 0);
+            ATTN_TRACE(14, gs);
+            umma_commit(&sfull[bsel]);
           }
+          __syncwarp();
         }
-        if (lane == 0) ATTN_TRACE(3, gs);    // MMA warp: dQ issued, dK / dV accumulator free
-        if (elect_one()) {
-          // [dK | . ; . | dV]_kb (+)= [dS^T ; P^T] [Q_qt | dO_qt] : both operands MN-major, reduction over the 128 queries
-#pragma unroll
-          for (int kk = 0; kk < kBQ / 16; ++kk)
-            umma_bf16_lo(tm_dkv, dsp_mn + kk * kStep16, qdo_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
-          umma_commit(&pfree[bsel]);
-          if (j == nq - 1) {
-            umma_commit(kvfull);
-            umma_commit(&kfree[kb]);
-          }
-          if (kb == nkb - 1) umma_commit(&qfree[sl]);
-          if (s == nsteps - 1) umma_commit(dqfull);
-        }
-        __syncwarp();
-        if (lane == 0) ATTN_TRACE(4, gs);    // MMA warp: gradient MMAs of step gs issued
-        if (ahead.w < total && g_ahead == gs + 1) issue_ahead();   // the next step must be under way: wait for its loads
+        g += (uint32_t)nsteps;
       }
-      g += (uint32_t)nsteps;
+    } else {
+      const uint32_t kDS_k = umma_desc_lo(aDS, 16);                                             // K-major
+      const uint32_t kK_mn = umma_desc_lo(aK, 16384);                                           // MN-major
+      // stacked operands of the dK / dV product: 128 rows = 64 of dS^T then 64 of P^T; 128 columns = 64 of Q then 64 of dO
+      const uint32_t kDSP_mn = umma_desc_lo(aDS, AttnBwdShortSmem::kP - AttnBwdShortSmem::kDS);
+      const uint32_t kQDO_mn = umma_desc_lo(aQ, AttnBwdShortSmem::kDO - AttnBwdShortSmem::kQ);
+      const uint32_t id_dq = umma_idesc_bf16(kBQ, kDH, 0, 1), id_dkv = umma_idesc_bf16(128, 128, 1, 1);
+      const uint32_t tm_dq = tmem_base + 256, tm_dkv = tmem_base + 384;
+      int it = 0;
+      uint32_t g = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        for (int s = 0; s < nsteps; ++s) {
+          int kb, j, qt;
+          decode(s, kb, j, qt);
+          const uint32_t gs = g + s, bsel = gs & 1u;
+          const int sl = qslot(it, qt);
+          const int nk16 = (kb == nkb - 1 ? ncols_tail : kKB) >> 4;
+          mbar_wait(&pfull[bsel], (gs >> 1) & 1u);
+          if (lane == 0) ATTN_TRACE(1, gs);    // P / dS of step gs received
+          if (s == 0 && it > 0) mbar_wait(dqfree, (uint32_t)(it - 1) & 1u);   // the previous item's dQ has been read out
+          tc_fence_after();
+          const uint32_t ds_k = kDS_k + bsel * kSlot, k_mn = kK_mn + kb * kBlk;
+          const uint32_t dsp_mn = kDSP_mn + bsel * kSlot, qdo_mn = kQDO_mn + sl * kSlot;
+          if (elect_one()) {
+            // dQ_qt (+)= dS K_kb : A = dS K-major (M = 128 queries, K = keys), B = K_kb MN-major (N = 64)
+#pragma unroll
+            for (int kk = 0; kk < kKB / 16; ++kk)
+              if (kk < nk16) umma_bf16_lo(tm_dq + qt * 64, ds_k + 2 * kk, k_mn + kk * kStep16, id_dq, (kb > 0 || kk > 0));
+          }
+          __syncwarp();
+          if (j == 0) {
+            const int ckv = it * nkb + kb;   // key blocks completed so far
+            if (ckv > 0) {
+              mbar_wait(kvfree, (uint32_t)(ckv - 1) & 1u);   // dK / dV of the previous key block have been read out
+              tc_fence_after();
+            }
+          }
+          if (lane == 0) ATTN_TRACE(3, gs);    // dQ issued, dK / dV accumulator free
+          if (elect_one()) {
+            // [dK | . ; . | dV]_kb (+)= [dS^T ; P^T] [Q_qt | dO_qt] : both operands MN-major, reduction over the 128 queries
+#pragma unroll
+            for (int kk = 0; kk < kBQ / 16; ++kk)
+              umma_bf16_lo(tm_dkv, dsp_mn + kk * kStep16, qdo_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
+            umma_commit(&pfree[bsel]);
+            if (j == nq - 1) umma_commit(&kfree[kb]);   // K / V block free AND dK / dV of the block complete
+            if (kb == nkb - 1) umma_commit(&qfree[sl]);
+            if (s == nsteps - 1) umma_commit(dqfull);
+          }
+          __syncwarp();
+          if (lane == 0) ATTN_TRACE(4, gs);    // gradient MMAs of step gs issued
+        }
+        g += (uint32_t)nsteps;
+      }
     }
+  } else if (warp >= 20) {
+    // warp 21: padding so that the MMA issuers land on sub-partitions 2 and 3
   } else if (warp >= 16) {
     // ---------------------------------------------------------------- read-out warps (one per TMEM lane quadrant)
     const int quad = warp & 3;
@@ -1195,7 +1198,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
       const int h = w % H, b = w / H;
       for (int kb = 0; kb < nkb; ++kb) {
         const int ckv = it * nkb + kb;
-        mbar_wait(kvfull, (uint32_t)ckv & 1u);
+        mbar_wait(&kfree[kb], (uint32_t)it & 1u);
         if (warp == 16 && lane == 0) ATTN_TRACE(5, ckv);   // read-out: dK / dV of key block ckv complete
         tc_fence_after();
         // lanes 0-63 (quadrants 0, 1): dK rows in columns 0-63; lanes 64-127: dV rows in columns 64-127
@@ -1352,7 +1355,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 20) tmem_dealloc(tmem_base, 512);
+  if (warp == kBwdShortMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 static int make_tok_tmap(CUtensorMap* m, const void* base, int B, int N, int row_elems, int box_rows = 128) {
@@ -1513,14 +1516,11 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
 
 #ifdef VS_ATTN_TRACE
 extern "C" int vs_debug_attn_trace(unsigned long long* host, int cap) {
-  unsigned int n = 0;
+  if (cap < (4 << 13)) return -1;
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, g_attn_trace_n, sizeof(n));
-  if ((int)n > cap) n = cap;
-  if (n > (1u << 16)) n = 1u << 16;
-  cudaMemcpyFromSymbol(host, g_attn_trace, n * sizeof(unsigned long long));
-  unsigned int zero = 0;
-  cudaMemcpyToSymbol(g_attn_trace_n, &zero, sizeof(zero));
-  return (int)n;
+  cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (4 << 13));
+  static unsigned long long zeros[4 << 13];
+  cudaMemcpyToSymbol(g_attn_trace, zeros, sizeof(zeros));
+  return 4 << 13;
 }
 #endif
