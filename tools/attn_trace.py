@@ -28,15 +28,15 @@ K.attention_fwd(qkv, ctx, lse, B, N, H, 0.125, dropout=drop)
 lib = _lib.load()
 lib.vs_debug_attn_trace.argtypes = [C.c_void_p, C.c_int]
 lib.vs_debug_attn_trace.restype = C.c_int
-buf = (C.c_ulonglong * 32768)()
+buf = (C.c_ulonglong * 49152)()
 for _ in range(3):
     K.attention_bwd(qkv, ctx, dctx, lse, dqkv, None, delta, B, N, H, 0.125, dropout=drop)
-    n = lib.vs_debug_attn_trace(buf, 32768)
+    n = lib.vs_debug_attn_trace(buf, 49152)
 ev = sorted(((buf[i] & 0xFFFFFFFFFF, buf[i] >> 56, (buf[i] >> 40) & 0xFFFF) for i in range(n) if buf[i] != 0))
 n = len(ev)
 t0 = ev[0][0]
-names = {1: "mma:pfull", 2: "mma:ahead", 3: "mma:dq+kvfree", 4: "mma:grads", 5: "drain:kvfull", 6: "drain:kvfree",
-         12: "mma:sdp_begin", 13: "mma:sdp_ops_ok", 14: "mma:sdp_issued", 15: "mma:sdp_commit", 7: "cmp:wait_s", 8: "cmp:got_s", 9: "cmp:chunk0", 10: "cmp:got_buf", 11: "cmp:pfull"}
+names = {1: "grad:pfull", 2: "mma:ahead", 3: "grad:dq+kvfree", 4: "grad:issued", 5: "drain:kvfull", 6: "drain:kvfree",
+         12: "sdp:begin", 13: "sdp:ready", 14: "sdp:issued", 15: "sdp:commit", 7: "cmp:wait_s", 8: "cmp:got_s", 9: "cmp:chunk0", 10: "cmp:got_buf", 11: "cmp:pfull"}
 print(f"{n} events")
 for t, e, s in ev:
     print(f"{t - t0:8d} {names.get(e, e):14s} step {s}")

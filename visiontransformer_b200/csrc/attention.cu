@@ -975,13 +975,13 @@ __device__ __forceinline__ void bwd_chunk16(const uint32_t (&sv)[16], const uint
 // -DVS_ATTN_TRACE: CTA 0 records (event, global step, clock) triples of its control flow — the timeline tool used to
 // find where the step period of this kernel goes (tools/attn_trace.py).  Not compiled into the shipped library.
 #ifdef VS_ATTN_TRACE
-// four tracing threads (MMA warp, read-out warp 16, compute warps 0 and 8; lane 0 each), each with a private slice and a
+// five tracing threads (the two MMA warps, read-out warp 16, compute warps 0 and 8; lane 0 each), each with a private slice and a
 // private counter: a record costs one clock read and one fire-and-forget store
-__device__ unsigned long long g_attn_trace[4 << 13];
+__device__ unsigned long long g_attn_trace[6 << 13];
 __device__ __forceinline__ void attn_trace(int ev, unsigned step, unsigned& n) {
   if (blockIdx.x != 0 || n >= (1u << 13)) return;
   const int warp = threadIdx.x >> 5;
-  const int role = warp >= kBwdShortMmaWarp - 1 ? 0 : (warp >= 16 ? 1 : (warp < 8 ? 2 : 3));
+  const int role = warp == kBwdShortMmaWarp ? 0 : (warp == kBwdShortMmaWarp - 1 ? 4 : (warp >= 16 ? 1 : (warp < 8 ? 2 : 3)));
   g_attn_trace[role * (1 << 13) + n++] = ((unsigned long long)ev << 56) | ((unsigned long long)(step & 0xFFFFu) << 40) |
                                          ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
 }
@@ -1151,17 +1151,22 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
           const int nk16 = (kb == nkb - 1 ? ncols_tail : kKB) >> 4;
           mbar_wait(&pfull[bsel], (gs >> 1) & 1u);
           if (lane == 0) ATTN_TRACE(1, gs);    // P / dS of step gs received
-          if (s == 0 && it > 0) mbar_wait(dqfree, (uint32_t)(it - 1) & 1u);   // the previous item's dQ has been read out
           tc_fence_after();
           const uint32_t ds_k = kDS_k + bsel * kSlot, k_mn = kK_mn + kb * kBlk;
           const uint32_t dsp_mn = kDSP_mn + bsel * kSlot, qdo_mn = kQDO_mn + sl * kSlot;
-          if (elect_one()) {
+          auto issue_dq = [&]() {
             // dQ_qt (+)= dS K_kb : A = dS K-major (M = 128 queries, K = keys), B = K_kb MN-major (N = 64)
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < kKB / 16; ++kk)
-              if (kk < nk16) umma_bf16_lo(tm_dq + qt * 64, ds_k + 2 * kk, k_mn + kk * kStep16, id_dq, (kb > 0 || kk > 0));
-          }
-          __syncwarp();
+              for (int kk = 0; kk < kKB / 16; ++kk)
+                if (kk < nk16) umma_bf16_lo(tm_dq + qt * 64, ds_k + 2 * kk, k_mn + kk * kStep16, id_dq, (kb > 0 || kk > 0));
+            }
+            __syncwarp();
+          };
+          // the first step of an item: the previous item's dQ may still be on its way out (r02 timeline: ~4000 cycles
+          // from the item's last MMA to the end of its dQ read-out), so the dK / dV MMAs go first there
+          const bool dq_last = s == 0 && it > 0;
+          if (!dq_last) issue_dq();
           if (j == 0) {
             const int ckv = it * nkb + kb;   // key blocks completed so far
             if (ckv > 0) {
@@ -1169,12 +1174,20 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
               tc_fence_after();
             }
           }
-          if (lane == 0) ATTN_TRACE(3, gs);    // dQ issued, dK / dV accumulator free
+          if (lane == 0) ATTN_TRACE(3, gs);    // dK / dV accumulator free
           if (elect_one()) {
             // [dK | . ; . | dV]_kb (+)= [dS^T ; P^T] [Q_qt | dO_qt] : both operands MN-major, reduction over the 128 queries
 #pragma unroll
             for (int kk = 0; kk < kBQ / 16; ++kk)
               umma_bf16_lo(tm_dkv, dsp_mn + kk * kStep16, qdo_mn + kk * kStep16, id_dkv, (j > 0 || kk > 0));
+          }
+          __syncwarp();
+          if (dq_last) {
+            mbar_wait(dqfree, (uint32_t)(it - 1) & 1u);   // the previous item's dQ has been read out
+            tc_fence_after();
+            issue_dq();
+          }
+          if (elect_one()) {
             umma_commit(&pfree[bsel]);
             if (j == nq - 1) umma_commit(&kfree[kb]);   // K / V block free AND dK / dV of the block complete
             if (kb == nkb - 1) umma_commit(&qfree[sl]);
@@ -1240,7 +1253,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
         __nv_bfloat16* dst = dqkv + ((size_t)b * N + q) * (3 * D) + h * kDH;
         const uint32_t src = tm_dq + qt * 64 + lane_off;
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
+        for (int c2 = 0; c2 < 2; ++c2) {   // 32 columns per TMEM round trip (64 at once spill at this kernel's 80 registers)
           uint32_t va[16], vb[16];
           if (live) {
             tmem_ld16(src + c2 * 32, va);
@@ -1516,11 +1529,11 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
 
 #ifdef VS_ATTN_TRACE
 extern "C" int vs_debug_attn_trace(unsigned long long* host, int cap) {
-  if (cap < (4 << 13)) return -1;
+  if (cap < (6 << 13)) return -1;
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (4 << 13));
-  static unsigned long long zeros[4 << 13];
+  cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (6 << 13));
+  static unsigned long long zeros[6 << 13];
   cudaMemcpyToSymbol(g_attn_trace, zeros, sizeof(zeros));
-  return 4 << 13;
+  return 6 << 13;
 }
 #endif
