@@ -33,7 +33,7 @@ def t(name, fn, reps=30):
     print(f"{name:44s} {ms*1e3:7.1f} us  {2.0*M*N*Kd/ms/1e9:7.1f} TFLOP/s", flush=True)
 
 
-for cfg in (0, 1, 2, 3, 4):
+for cfg in [int(c) for c in os.environ.get("EPI_CFGS", "0,1,2,3,4").split(",")]:
     print("tile_cfg", cfg)
     t("plain bf16", lambda: K.gemm(a, w, out, tile_cfg=cfg))
     t("bias", lambda: K.gemm(a, w, out, bias=bias, tile_cfg=cfg))

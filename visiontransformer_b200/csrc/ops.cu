@@ -2,6 +2,8 @@
 //   bias-gradient column sums, patch extraction, CLS/position rows, embedding backward, segmentation-head
 //   im2col / col2im, the 1x1 classifier conv (forward + backward with fused ReLU'), weight casts / packing.
 // Reference anchors: TF:100-128,153-167 (embeddings); model/CE/classes.py:240-244,250-257 (seg head).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/vitseg.h"
 
@@ -91,24 +93,27 @@ colsum_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int M, int N, float*
 // ------------------------------------------------------------------------------------------------
 // patchify: NCHW fp32 image -> bf16 [B*T, 3*P*P] with K = (c, ph, pw); 4 pixels per thread
 // ------------------------------------------------------------------------------------------------
-__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int P) {
+// One block per (image, patch row): consecutive threads walk a full image line (coalesced 16-byte reads), and the
+// index arithmetic is 32-bit with one decode per element (the flat 64-bit grid-stride form spent 68 % of its issue slots
+// on five 64-bit divisions per vector: 25 us for 58 MB, ncu r02 step table).
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int P) {
   pdl_wait();
   pdl_trigger();
   const int gp = S / P;
   const int K = 3 * P * P;
-  const long long total = (long long)B * gp * gp * (K / 4);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int k4 = int(idx % (K / 4));
-    const long long row = idx / (K / 4);
-    const int k = k4 * 4;
-    const int c = k / (P * P), rem = k - c * P * P, ph = rem / P, pw = rem - ph * P;
-    const int tx = int(row % gp);
-    const long long t2 = row / gp;
-    const int ty = int(t2 % gp), b = int(t2 / gp);
-    const float4 v = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + c) * S + (ty * P + ph)) * S + tx * P + pw);
-    const long long orow = (long long)b * (gp * gp + 1) + 1 + ty * gp + tx;
-    *reinterpret_cast<uint2*>(out + orow * K + k) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  const int S4 = S / 4;
+  const int b = blockIdx.x / gp, ty = blockIdx.x - b * gp;
+  const int n = 3 * P * S4;   // (channel, line within the patch row, 4-pixel group)
+  const float* src = img + ((long long)b * 3 * S + (long long)ty * P) * S;
+  __nv_bfloat16* dst = out + ((long long)b * (gp * gp + 1) + 1 + (long long)ty * gp) * K;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int line = i / S4, x = (i - line * S4) * 4;
+    const int c = line / P, ph = line - c * P;
+    const int tx = x / P, pw = x - tx * P;
+    const float4 v = *reinterpret_cast<const float4*>(src + ((long long)c * S + ph) * S + x);
+    *reinterpret_cast<uint2*>(dst + (long long)tx * K + c * P * P + ph * P + pw) =
+        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
 }
 
@@ -132,7 +137,17 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict
   if (idx >= T1 * D4) return;
   float4 s = make_float4(0, 0, 0, 0);
   const float4* p = reinterpret_cast<const float4*>(dx) + idx;
-  for (int b = 0; b < B; ++b) {
+  // eight independent loads in flight per thread (the grid is only T1 * D / 4 threads, about one block per SM: with a
+  // plain dependent loop the kernel ran at 1.7 TB/s, r02 step table)
+  int b = 0;
+  for (; b + 8 <= B; b += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = p[(long long)(b + u) * T1 * D4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+  }
+  for (; b < B; ++b) {
     const float4 v = p[(long long)b * T1 * D4];
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
@@ -154,26 +169,30 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, float* __restrict
 // ------------------------------------------------------------------------------------------------
 // seg head: im2col of the token grid (CLS dropped), 3x3 window, zero padding; K = (ky, kx, c)
 // ------------------------------------------------------------------------------------------------
-__global__ void head_im2col_kernel(const __nv_bfloat16* __restrict__ tok, __nv_bfloat16* __restrict__ col, int B, int g,
-                                   int D) {
+// One warp per (pixel, tap): the 2*D-byte source row and destination slice are both contiguous, so a lane moves 16-byte
+// vectors at a fixed stride and the only index arithmetic is one pixel decode per block iteration.  (The first version
+// was a flat grid-stride loop with five 64-bit divisions per 16-byte vector: 79 us = 2.2 TB/s for 173 MB written,
+// 73 % issue-bound — ncu r02 step table.)
+__global__ void __launch_bounds__(288)
+head_im2col_kernel(const __nv_bfloat16* __restrict__ tok, __nv_bfloat16* __restrict__ col, int B, int g, int D) {
   pdl_wait();
   pdl_trigger();
   const int D8 = D / 8;
-  const long long total = (long long)B * g * g * 9 * D8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = int(idx % D8);
-    long long r = idx / D8;
-    const int kk = int(r % 9);
-    r /= 9;
-    const int x = int(r % g);
-    r /= g;
-    const int y = int(r % g), b = int(r / g);
-    const int yy = y + kk / 3 - 1, xx = x + kk % 3 - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (yy >= 0 && yy < g && xx >= 0 && xx < g)
-      v = *reinterpret_cast<const uint4*>(tok + ((long long)b * (g * g + 1) + 1 + yy * g + xx) * D + c8 * 8);
-    *reinterpret_cast<uint4*>(col + (((long long)b * g + y) * g + x) * (9LL * D) + (long long)kk * D + c8 * 8) = v;
+  const int kk = threadIdx.x >> 5, lane = threadIdx.x & 31;   // 9 warps = the 9 taps
+  const int dy = kk / 3 - 1, dx = kk % 3 - 1;
+  const int npix = B * g * g;
+  for (int pix = blockIdx.x; pix < npix; pix += gridDim.x) {
+    const int b = pix / (g * g), t = pix - b * g * g;
+    const int y = t / g, x = t - y * g;
+    const int yy = y + dy, xx = x + dx;
+    const bool in = yy >= 0 && yy < g && xx >= 0 && xx < g;
+    const uint4* src = reinterpret_cast<const uint4*>(tok + ((long long)b * (g * g + 1) + 1 + yy * g + xx) * D);
+    uint4* dst = reinterpret_cast<uint4*>(col + (long long)pix * (9LL * D) + (long long)kk * D);
+    if (in) {
+      for (int c8 = lane; c8 < D8; c8 += 32) dst[c8] = src[c8];
+    } else {
+      for (int c8 = lane; c8 < D8; c8 += 32) dst[c8] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 
@@ -524,8 +543,8 @@ extern "C" int vs_patchify(const float* img, void* out, int32_t B, int32_t S, in
   VS_CHECK_ARG(img && out && B > 0 && S > 0 && P >= 4 && P % 4 == 0 && S % P == 0, "vs_patchify: bad arguments");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_patchify: no CUDA device");
-  const long long total = (long long)B * (S / P) * (S / P) * (3 * P * P / 4);
-  launch_k(patchify_kernel, dim3(grid_for(total, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, img, (__nv_bfloat16*)out, B, S, P);
+  VS_CHECK_ARG((long long)B * (S / P) < (1LL << 31), "vs_patchify: too many patch rows");
+  launch_k(patchify_kernel, dim3((unsigned)(B * (S / P))), dim3(256), (size_t)(0), (cudaStream_t)stream, img, (__nv_bfloat16*)out, B, S, P);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -552,8 +571,10 @@ extern "C" int vs_head_im2col(const void* tokens, void* col, int32_t B, int32_t 
   VS_CHECK_ARG(tokens && col && B > 0 && g > 0 && D % 8 == 0, "vs_head_im2col: bad arguments");
   const int nsm = sm_count();
   VS_CHECK_ARG(nsm > 0, "vs_head_im2col: no CUDA device");
-  const long long total = (long long)B * g * g * 9 * (D / 8);
-  launch_k(head_im2col_kernel, dim3(grid_for(total, 256, nsm)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)tokens, (__nv_bfloat16*)col, B, g, D);
+  const long long npix = (long long)B * g * g;
+  VS_CHECK_ARG(npix < (1LL << 31), "vs_head_im2col: too many pixels");
+  const long long grid = npix < (long long)nsm * 7 ? npix : (long long)nsm * 7;   // 7 blocks of 288 threads per SM
+  launch_k(head_im2col_kernel, dim3((unsigned)grid), dim3(288), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)tokens, (__nv_bfloat16*)col, B, g, D);
   VS_CHECK_LAUNCH();
   return 0;
 }
@@ -582,6 +603,8 @@ extern "C" int vs_conv1x1_fwd(const void* feat, const float* w, const float* b, 
     smem_set = smem;
   }
   const long long npix = (long long)B * g * g;
+  // 8 blocks per SM: the warp-per-pixel loop is latency-bound (a 5-step shuffle reduction per class), so occupancy wins
+  // over amortising the per-block weight staging (r02 s25: 2 blocks per SM measured 39.8 us against 32.5 us)
   int grid = (int)((npix + 7) / 8);
   if (grid > nsm * 8) grid = nsm * 8;
   launch_k(conv1x1_fwd_kernel, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, (const __nv_bfloat16*)feat, w, b, logits, B, g * g, F, C);
@@ -598,7 +621,15 @@ extern "C" int vs_conv1x1_bwd(const float* dlogits, const void* feat, const floa
   VS_CHECK_ARG(nsm > 0, "vs_conv1x1_bwd: no CUDA device");
   const long long npix = (long long)B * g * g;
   VS_CHECK_ARG((uintptr_t)dw % 16 == 0, "vs_conv1x1_bwd: dw must be 16-byte aligned");
-  int grid = nsm;
+  // two blocks per SM (r02 s25, cold L2: 50.5 us with one, 41.2 us with two or three, 62 us with four — more blocks
+  // shorten each block's serial pixel loop but multiply the same-address dW reductions); VS_C1B_BLOCKS_PER_SM overrides
+  static int bwd_mult = -1;
+  if (bwd_mult < 0) {
+    const char* e = getenv("VS_C1B_BLOCKS_PER_SM");
+    bwd_mult = e ? atoi(e) : 2;
+    if (bwd_mult < 1 || bwd_mult > 4) bwd_mult = 2;
+  }
+  int grid = nsm * bwd_mult;
   if (grid > (npix + 63) / 64) grid = (int)((npix + 63) / 64);
   launch_k(conv1x1_bwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, dlogits, (const __nv_bfloat16*)feat, w, (__nv_bfloat16*)dfeat, dw, db, B, g * g, F, C);
   VS_CHECK_LAUNCH();
