@@ -73,3 +73,9 @@ tf("head_col2im", lambda: K.head_col2im(col, dtok, B, g, D))
 tf("conv1x1_fwd", lambda: K.conv1x1_fwd(feat, w, bias, low, B, g, F, C))
 tf("conv1x1_bwd", lambda: K.conv1x1_bwd(dlow, feat, w, dfeat, dw, db, B, g, F, C))
 tf("embed_bwd", lambda: K.embed_bwd(dx, dcls, dpos, dpb, B, T1, D))
+labels = torch.randint(0, C, (B, 256, 256), device=dev)
+loss_sum = torch.zeros(2, device=dev)
+dlo = torch.zeros(B, C, g, g, device=dev)
+tf("upsample_ce (int64 labels 256x256)", lambda: K.upsample_ce(low, labels, loss_sum, dlo, S))
+mask8 = torch.empty(B, S, S, device=dev, dtype=torch.uint8)
+tf("upsample_argmax", lambda: K.upsample_argmax(low, mask8))

@@ -595,10 +595,11 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
       acc = fmaf(a1, g1, acc);
     }
   }
-  const int hh = int(row % H);
-  const long long bn = row / H;
-  const int n = int(bn % N);
-  const int bb = int(bn / N);
+  // 32-bit index arithmetic (the host checks B * N * H < 2^31): three 64-bit divisions cost more instructions than the
+  // 64-element dot product itself
+  const unsigned r32 = (unsigned)row;
+  const unsigned bn = r32 / (unsigned)H, hh = r32 - bn * (unsigned)H;
+  const unsigned bb = bn / (unsigned)N, n = bn - bb * (unsigned)N;
   delta[((size_t)bb * H + hh) * N + n] = acc;
 }
 
@@ -1488,6 +1489,7 @@ extern "C" int vs_attention_bwd(const void* qkv, const void* ctx, const void* dc
   if (int rc2 = make_drop(&dc, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
   {
     const long long rows = (long long)B * N * H;
+    VS_CHECK_ARG(rows < (1LL << 31), "vs_attention_bwd: B * N * H must be < 2^31");
     launch_k(attn_delta_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), (size_t)(0), st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, delta, dq_accum, B, N, H);
     VS_CHECK_LAUNCH();
   }

@@ -210,7 +210,7 @@ upsample_argmax_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask
 // cross-entropy, the column-constant part of the bilinear interpolation is hoisted: z_c(y, x) = ly0 * a_c + ly1 * b_c with
 // a_c, b_c in registers, so a pixel costs 2 FMAs + a compare/select pair per class instead of 4 shared-memory reads and
 // ~12 instructions (r01: the fused mask path was SLOWER than writing 218 MB of logits and taking their argmax).
-template <int CMAX>
+template <int CMAX, bool kExact>
 __global__ void __launch_bounds__(256)
 upsample_argmax_region_kernel(const float* __restrict__ low, uint8_t* __restrict__ mask, int B, int C, int g, int S) {
   pdl_wait();
@@ -245,7 +245,7 @@ upsample_argmax_region_kernel(const float* __restrict__ low, uint8_t* __restrict
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) {
     a[c] = 0.0f; bq[c] = 0.0f;
-    if (c < C) {
+    if (kExact || c < C) {
       a[c] = lx0 * s_cell[warp][0][c] + lx1 * s_cell[warp][1][c];
       bq[c] = lx0 * s_cell[warp][2][c] + lx1 * s_cell[warp][3][c];
     }
@@ -261,7 +261,7 @@ upsample_argmax_region_kernel(const float* __restrict__ low, uint8_t* __restrict
       float best = -INFINITY;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c) {
-        if (c < C) {
+        if (kExact || c < C) {
           const float v = ly0 * a[c] + ly1 * bq[c];
           if (v > best) { best = v; bi = c; }
         }
@@ -398,7 +398,10 @@ struct CeCfg {
   static constexpr int kPad = 36;   // floats per row of the reduction tile: LDS.128 of a quarter-warp stays conflict-free
 };
 
-template <int CMAX, typename LabelT>
+// kExact: C == CMAX, so the per-class `c < C` tests vanish at compile time.  With a runtime C the compiler cannot keep 17
+// class predicates alive across the pixel loop and re-derives them in every phase of every pixel (SASS r02: 17 ISETP +
+// 17 FSEL + 33 LOP3 in the max phase alone; 340 instructions per pixel, of which the mathematics needs ~190).
+template <int CMAX, typename LabelT, bool kExact>
 __global__ void __launch_bounds__(CeCfg<CMAX>::kWarps * 32)
 upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ labels, int LH, int LW, float lab_sy,
                    float lab_sx, float* __restrict__ loss_sum, float* __restrict__ dlow, int B, int C, int g, int S) {
@@ -424,7 +427,7 @@ upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ lab
     bil_coord(r.y_lo, scale, g, y0, y1, t0, t1);
     bil_coord(r.x_lo, scale, g, x0, x1, t0, t1);
     const float* lb = low + (long long)r.b * C * g * g;
-    for (int c = lane; c < C; c += 32) {
+    for (int c = lane; c < (kExact ? CMAX : C); c += 32) {
       s_cell[warp][0][c] = lb[c * g * g + y0 * g + x0];
       s_cell[warp][1][c] = lb[c * g * g + y0 * g + x1];
       s_cell[warp][2][c] = lb[c * g * g + y1 * g + x0];
@@ -447,7 +450,7 @@ upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ lab
     for (int c = 0; c < CMAX; ++c) {
       acc0[c] = 0.0f; acc1[c] = 0.0f;
       a[c] = 0.0f; bq[c] = 0.0f;
-      if (c < C) {
+      if (kExact || c < C) {
         // PyTorch's association order: ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11); log2(e) folded in afterwards
         a[c] = (lx0 * s_cell[warp][0][c] + lx1 * s_cell[warp][1][c]) * kLog2e;
         bq[c] = (lx0 * s_cell[warp][2][c] + lx1 * s_cell[warp][3][c]) * kLog2e;
@@ -471,7 +474,7 @@ upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ lab
         float m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-          if (c < C) {
+          if (kExact || c < C) {
             z[c] = ly0 * a[c] + ly1 * bq[c];     // log2(e) * logit
             m = fmaxf(m, z[c]);
           }
@@ -479,7 +482,7 @@ upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ lab
         float ssum = 0.0f;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-          if (c < C) {
+          if (kExact || c < C) {
             float e;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z[c] - m));
             z[c] = e;
@@ -500,7 +503,7 @@ upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ lab
           const float w0 = ly0 * inv, w1 = ly1 * inv;
 #pragma unroll
           for (int c = 0; c < CMAX; ++c) {
-            if (c < C) {
+            if (kExact || c < C) {
               acc0[c] = fmaf(z[c], w0, acc0[c]);
               acc1[c] = fmaf(z[c], w1, acc1[c]);
             }
@@ -513,7 +516,7 @@ upsample_ce_kernel(const float* __restrict__ low, const LabelT* __restrict__ lab
     if (dlow != nullptr) {
 #pragma unroll
       for (int c = 0; c < CMAX; ++c) {
-        if (c < C) {
+        if (kExact || c < C) {
           s_acc[warp][2 * c][lane] += acc0[c];
           s_acc[warp][2 * c + 1][lane] += acc1[c];
         }
@@ -1028,10 +1031,16 @@ extern "C" int vs_upsample_argmax(const float* low, uint8_t* mask, int32_t B, in
     const long long nreg = (long long)B * (g + 1) * (g + 1);
     const unsigned grid = (unsigned)((nreg + 7) / 8);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 1) launch_k(upsample_argmax_region_kernel<1>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
-    else if (C <= 8) launch_k(upsample_argmax_region_kernel<8>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
-    else if (C <= 17) launch_k(upsample_argmax_region_kernel<17>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
-    else launch_k(upsample_argmax_region_kernel<32>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);
+#define VS_AM_LAUNCH(CM)                                                                                              \
+  do {                                                                                                                \
+    if (C == CM) launch_k(upsample_argmax_region_kernel<CM, true>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S); \
+    else launch_k(upsample_argmax_region_kernel<CM, false>, dim3(grid), dim3(256), (size_t)0, st, low, mask, B, C, g, S);        \
+  } while (0)
+    if (C == 1) VS_AM_LAUNCH(1);
+    else if (C <= 8) VS_AM_LAUNCH(8);
+    else if (C <= 17) VS_AM_LAUNCH(17);
+    else VS_AM_LAUNCH(32);
+#undef VS_AM_LAUNCH
     VS_CHECK_LAUNCH();
     return 0;
   }
@@ -1092,7 +1101,10 @@ static void launch_upsample_ce(const float* low, const void* labels, int LH, int
   const unsigned grid = (unsigned)((nreg + kWarps - 1) / kWarps);
   // the scale PyTorch's nearest kernel uses: (float)input_size / output_size
   const float sy = (float)LH / (float)S, sx = (float)LW / (float)S;
-  launch_k(upsample_ce_kernel<CMAX, LabelT>, dim3(grid), dim3(kWarps * 32), (size_t)(0), st, low, (const LabelT*)labels, LH, LW, sy, sx, loss_sum, dlow, B, C, g, S);
+  if (C == CMAX)
+    launch_k(upsample_ce_kernel<CMAX, LabelT, true>, dim3(grid), dim3(kWarps * 32), (size_t)(0), st, low, (const LabelT*)labels, LH, LW, sy, sx, loss_sum, dlow, B, C, g, S);
+  else
+    launch_k(upsample_ce_kernel<CMAX, LabelT, false>, dim3(grid), dim3(kWarps * 32), (size_t)(0), st, low, (const LabelT*)labels, LH, LW, sy, sx, loss_sum, dlow, B, C, g, S);
 }
 
 extern "C" int vs_upsample_ce(const float* low, const void* labels, int32_t label_dtype, int32_t LH, int32_t LW,
