@@ -218,7 +218,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)(b * H + h), drop_seed(drop)) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
     const float lds = log2f(dscale);
-    const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);  // pair index base
+    const uint32_t drow = (uint32_t)q * (uint32_t)((N + 3) >> 2);  // quad index base (drop_keep4)
     float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
     float o_acc[32];
 #pragma unroll
@@ -280,15 +280,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       float l_blk = 0.0f;
       uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(fmaf(sc[i], sl2, -m_off));
-        const float x1 = fmaf(sc[i + 1], sl2, -m_off);
-        const float p1 = (kPoly == 2 || (kPoly == 4 && (i & 2))) ? ex2_poly(x1) : ex2_approx(x1);
-        l_blk += p0 + p1;   // row sum in dropout-scaled units (the normaliser uses the un-dropped probabilities)
-        bool k0 = true, k1 = true;
-        if (drop.thresh != 0u)   // keys 2k, 2k+1 of a query row share one hash
-          drop_keep2(2u * (drow + (uint32_t)((kv0 + half * 32 + i) >> 1)), dseed, drop.thresh, k0, k1);
-        pk[i >> 1] = pack_bf16(k0 ? p0 : 0.0f, k1 ? p1 : 0.0f);
+      for (int i4 = 0; i4 < 32; i4 += 4) {
+        bool kp[4] = {true, true, true, true};
+        if (drop.thresh != 0u)   // keys 4k .. 4k+3 of a query row share one hash
+          drop_keep4(drow + (uint32_t)((kv0 + half * 32 + i4) >> 2), dseed, drop.thresh, kp);
+#pragma unroll
+        for (int i = i4; i < i4 + 4; i += 2) {
+          const float p0 = ex2_approx(fmaf(sc[i], sl2, -m_off));
+          const float x1 = fmaf(sc[i + 1], sl2, -m_off);
+          const float p1 = (kPoly == 2 || (kPoly == 4 && (i & 2))) ? ex2_poly(x1) : ex2_approx(x1);
+          l_blk += p0 + p1;   // row sum in dropout-scaled units (the normaliser uses the un-dropped probabilities)
+          pk[i >> 1] = pack_bf16(kp[i - i4] ? p0 : 0.0f, kp[i - i4 + 1] ? p1 : 0.0f);
+        }
       }
       // P_j -> bf16 smem (A operand of P·V): this thread's 32 keys = 4 x 16-byte slots of its 128-byte row.  P buffer
       // sb was last read by P_{j-2} V_{j-2}, whose completion this thread awaited when it folded O_{j-2}.
@@ -441,7 +444,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const float sl2 = scale * kLog2e;
     const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)(b * H + h), drop_seed(drop)) : 0u;
     const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
-    const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
+    const uint32_t drow = (uint32_t)q * (uint32_t)((N + 3) >> 2);
     // 16-column chunks [c_beg, c_end) of this thread's row: the two threads of a row split the key axis
     const int nch = NK >> 4;
     const int c_beg = half == 0 ? 0 : (nch + 1) >> 1;
@@ -502,12 +505,13 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
         uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          l_part += pe[i] + pe[i + 1];
-          bool k0 = true, k1 = true;
-          if (drop.thresh != 0u)   // keys 2k, 2k+1 of a query row share one hash
-            drop_keep2(2u * (drow + (uint32_t)((c * 16 + i) >> 1)), dseed, drop.thresh, k0, k1);
-          pk[i >> 1] = pack_bf16(k0 ? pe[i] : 0.0f, k1 ? pe[i + 1] : 0.0f);
+        for (int i = 0; i < 16; i += 4) {
+          l_part += (pe[i] + pe[i + 1]) + (pe[i + 2] + pe[i + 3]);
+          bool kp[4] = {true, true, true, true};
+          if (drop.thresh != 0u)   // keys 4k .. 4k+3 of a query row share one hash
+            drop_keep4(drow + (uint32_t)((c * 16 + i) >> 2), dseed, drop.thresh, kp);
+          pk[i >> 1] = pack_bf16(kp[0] ? pe[i] : 0.0f, kp[1] ? pe[i + 1] : 0.0f);
+          pk[(i >> 1) + 1] = pack_bf16(kp[2] ? pe[i + 2] : 0.0f, kp[3] ? pe[i + 3] : 0.0f);
         }
         uint8_t* tile = sP + (c >> 2) * 16384;
         const uint32_t slot = uint32_t(c & 3) * 2;
@@ -802,7 +806,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
         const uint32_t ph = qn & 1;
         const int q = i * kBQ + r;
         const bool q_ok = q < N;
-        const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
+        const uint32_t drow = (uint32_t)q * (uint32_t)((N + 3) >> 2);
         const float lse2 = lse_n * kLog2e, dlt = dlt_n;
         // all 32 query rows of this warp lie beyond the sequence (N = 197: the last quadrant of the second tile):
         // P = dS = 0 without reading S / dP, and no dQ rows to add
@@ -819,13 +823,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
             tmem_ld16(tm_dp + lane_off + c, dv);
             tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-              bool keep[2] = {true, true};
+            for (int k = 0; k < 16; k += 4) {
+              bool keep[4] = {true, true, true, true};
               if (drop.thresh != 0u)
-                drop_keep2(2u * (drow + (uint32_t)((kv0 + c + k) >> 1)), dseed, drop.thresh, keep[0], keep[1]);
-              float pdv[2], dsv[2];
+                drop_keep4(drow + (uint32_t)((kv0 + c + k) >> 2), dseed, drop.thresh, keep);
+              float pdv[4], dsv[4];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
+              for (int u = 0; u < 4; ++u) {
                 float pv = ex2_approx(__uint_as_float(sv[k + u]) * sl2 - lse2);
                 if (tail_block) pv = (c + k + u < nvalid_kv) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
                 // forward used P_drop = m*P/(1-p): dV needs P_drop, and dP arrives w.r.t. P_drop
@@ -834,7 +838,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_consta
                 dsv[u] = (pv * scale) * (__uint_as_float(dv[k + u]) * mk - dlt);
               }
               pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
+              pk[(k >> 1) + 1] = pack_bf16(pdv[2], pdv[3]);
               dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
+              dsk[(k >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
             }
           } else {
 #pragma unroll
@@ -947,15 +953,15 @@ constexpr int kBwdShortMmaWarp = 23;   // sub-partition 3: its compute warps own
 // are what the mathematics needs).  dS is produced WITHOUT the softmax scale: the read-out warps apply it to dQ and dK.
 template <bool kDrop, bool kTail>
 __device__ __forceinline__ void bwd_chunk16(const uint32_t (&sv)[16], const uint32_t (&dv)[16], float sl2, float l2, float dl,
-                                            float dscale, uint32_t thresh, uint32_t dseed, uint32_t elem0, int nvalid,
+                                            float dscale, uint32_t thresh, uint32_t dseed, uint32_t quad0, int nvalid,
                                             uint32_t (&pk)[8], uint32_t (&dsk)[8]) {
 #pragma unroll
-  for (int k = 0; k < 16; k += 2) {
-    bool keep[2] = {true, true};
-    if (kDrop) drop_keep2(elem0 + (uint32_t)k, dseed, thresh, keep[0], keep[1]);
-    float pdv[2], dsv[2];
+  for (int k = 0; k < 16; k += 4) {
+    bool keep[4] = {true, true, true, true};
+    if (kDrop) drop_keep4(quad0 + (uint32_t)(k >> 2), dseed, thresh, keep);
+    float pdv[4], dsv[4];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 4; ++t) {
       float pv = ex2_approx(fmaf(__uint_as_float(sv[k + t]), sl2, -l2));
       if (kTail) pv = (k + t < nvalid) ? pv : 0.0f;   // zero-filled key rows give s = 0, not -inf
       if (kDrop) {
@@ -969,7 +975,9 @@ __device__ __forceinline__ void bwd_chunk16(const uint32_t (&sv)[16], const uint
       }
     }
     pk[k >> 1] = pack_bf16(pdv[0], pdv[1]);
+    pk[(k >> 1) + 1] = pack_bf16(pdv[2], pdv[3]);
     dsk[k >> 1] = pack_bf16(dsv[0], dsv[1]);
+    dsk[(k >> 1) + 1] = pack_bf16(dsv[2], dsv[3]);
   }
 }
 
@@ -1324,7 +1332,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
         const int ncols = (nvalid_kv + 15) & ~15;
         const bool tail_block = nvalid_kv < kKB;
         const int q = qt * kBQ + r;
-        const uint32_t drow = (uint32_t)q * (uint32_t)((N + 1) >> 1);
+        const uint32_t drow = (uint32_t)q * (uint32_t)((N + 3) >> 2);
         const float l2 = qt == 0 ? lse2[0] : lse2[1], dl = qt == 0 ? dlt[0] : dlt[1];
         const bool warp_dead = qt * kBQ + quad * 32 >= N;   // no live query row in this warp: P = dS = 0
         if ((warp & 7) == 0 && lane == 0) ATTN_TRACE(7, gs);    // compute: waiting for S / dP of step gs
@@ -1340,11 +1348,11 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tmap_kv, const __grid_
             tmem_ld16(tm_s + lane_off + c, sv);
             tmem_ld16(tm_dp + lane_off + c, dv);
             tmem_ld_wait();
-            const uint32_t elem0 = 2u * (drow + (uint32_t)((kv0 + c) >> 1));
+            const uint32_t quad0 = drow + (uint32_t)((kv0 + c) >> 2);
             if (tail_block)
-              bwd_chunk16<kDrop, true>(sv, dv, sl2, l2, dl, dscale, drop.thresh, dseed, elem0, nvalid_kv - c, pk, dsk);
+              bwd_chunk16<kDrop, true>(sv, dv, sl2, l2, dl, dscale, drop.thresh, dseed, quad0, nvalid_kv - c, pk, dsk);
             else
-              bwd_chunk16<kDrop, false>(sv, dv, sl2, l2, dl, dscale, drop.thresh, dseed, elem0, 16, pk, dsk);
+              bwd_chunk16<kDrop, false>(sv, dv, sl2, l2, dl, dscale, drop.thresh, dseed, quad0, 16, pk, dsk);
           } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) { pk[k] = 0u; dsk[k] = 0u; }

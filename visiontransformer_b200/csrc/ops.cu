@@ -481,14 +481,14 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ out, long long n, int 
       drop_keep2((uint32_t)(i & ~1LL), sd, drop.thresh, k0, k1);
       keep = (i & 1) ? k1 : k0;
     } else {
-      // attention probabilities [B*H*N rows, row_len = N]: keys 2k, 2k+1 of query q share hash(q * ceil(N/2) + k)
+      // attention probabilities [B*H*N rows, row_len = N]: keys 4k .. 4k+3 of query q share hash(q * ceil(N/4) + k)
       const long long row = i / row_len;
       const int kv = int(i - row * row_len);
-      bool k0, k1;
+      bool k4[4];
       // rows are (batch*head, query) with row_len queries per (batch, head): per-(batch, head) seed, as the kernels
       const uint32_t bh = (uint32_t)(row / row_len), q = (uint32_t)(row - (long long)bh * row_len);
-      drop_keep2(2u * (q * (uint32_t)((row_len + 1) >> 1) + (uint32_t)(kv >> 1)), drop_hash(bh, sd), drop.thresh, k0, k1);
-      keep = (kv & 1) ? k1 : k0;
+      drop_keep4(q * (uint32_t)((row_len + 3) >> 2) + (uint32_t)(kv >> 2), drop_hash(bh, sd), drop.thresh, k4);
+      keep = k4[kv & 3];
     }
     out[i] = keep ? 1 : 0;
   }
