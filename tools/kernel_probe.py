@@ -367,6 +367,42 @@ def probe_head():
         report("embed_bwd dpos", rel(dpos, dx.sum(0)), 1e-5)
         report("embed_bwd dcls", rel(dcls, dx[:, 0].sum(0)), 1e-5)
         report("embed_bwd dbias (patch rows only)", rel(dbp, dx[:, 1:].sum((0, 1))), 1e-5)
+        # rewritten glue kernels at other shapes: batch above / not a multiple of the 8-way unrolled loop of embed_bwd,
+        # patch 8 / patch 4 / 384-pixel patchify, im2col with 128 / 1024 channels and a 24 x 24 grid
+        for Bq, Tq, Dq in ((19, 50, 256), (8, 197, 128)):
+            dxq = torch.randn(Bq, Tq, Dq, device=dev)
+            dc, dp, dbq = torch.zeros(Dq, device=dev), torch.zeros(Tq, Dq, device=dev), torch.zeros(Dq, device=dev)
+            K.embed_bwd(dxq, dc, dp, dbq, Bq, Tq, Dq)
+            report(f"embed_bwd dpos B{Bq}", rel(dp, dxq.sum(0)), 1e-5)
+            report(f"embed_bwd dcls B{Bq}", rel(dc, dxq[:, 0].sum(0)), 1e-5)
+            report(f"embed_bwd dbias B{Bq}", rel(dbq, dxq[:, 1:].sum((0, 1))), 1e-5)
+        for Sq, Pq in ((224, 8), (224, 4), (384, 16), (64, 32)):
+            gq = Sq // Pq
+            imq = torch.rand(3, 3, Sq, Sq, device=dev)
+            pq = torch.zeros(3 * (gq * gq + 1), 3 * Pq * Pq, device=dev, dtype=torch.bfloat16)
+            K.patchify(imq, pq, Pq)
+            refq = F.unfold(imq, Pq, stride=Pq).transpose(1, 2)
+            report(f"patchify S{Sq} P{Pq}", rel(pq.view(3, gq * gq + 1, -1)[:, 1:], refq), 4e-3)
+            report(f"patchify S{Sq} P{Pq} cls rows untouched", pq.view(3, gq * gq + 1, -1)[:, 0].abs().max().item(), 0.0)
+        for Bq, gq, Dq in ((3, 24, 128), (1, 7, 1024), (5, 14, 768)):
+            Tq = gq * gq
+            tq = bf(torch.randn(Bq, Tq + 1, Dq, device=dev))
+            cq = torch.full((Bq * Tq, 9 * Dq), 7.0, device=dev, dtype=torch.bfloat16)
+            K.head_im2col(tq, cq, Bq, gq, Dq)
+            fq = tq[:, 1:].float().transpose(1, 2).reshape(Bq, Dq, gq, gq)
+            rq = F.unfold(fq, 3, padding=1).view(Bq, Dq, 9, Tq).permute(0, 3, 2, 1).reshape(Bq * Tq, 9 * Dq)
+            report(f"head im2col B{Bq} g{gq} D{Dq} (exact)", (cq.float() - rq).abs().max().item(), 0.0)
+        # conv1x1 backward over enough pixels for two blocks per SM
+        Bq = 48
+        ftq = bf(torch.relu(torch.randn(Bq * T, Fd, device=dev)))
+        dlq = torch.randn(Bq, Cn, g, g, device=dev)
+        dfq = torch.empty(Bq * T, Fd, device=dev, dtype=torch.bfloat16)
+        dwq, dbq2 = torch.zeros(Cn, Fd, device=dev), torch.zeros(Cn, device=dev)
+        K.conv1x1_bwd(dlq, ftq, w2, dfq, dwq, dbq2, Bq, g, Fd, Cn)
+        dlq2 = dlq.view(Bq, Cn, T).transpose(1, 2).reshape(Bq * T, Cn)
+        report("conv1x1 bwd dfeat B48", rel(dfq, (dlq2 @ w2) * (ftq.float() > 0)), 1e-2)
+        report("conv1x1 bwd dw B48", rel(dwq, dlq2.t() @ ftq.float()), 1e-4)
+        report("conv1x1 bwd db B48", rel(dbq2, dlq2.sum(0)), 1e-4)
         gpk = torch.randn(Fd, 9 * D, device=dev)
         dwc = torch.zeros(Fd, D, 3, 3, device=dev)
         K.unpack_conv3x3_grad(gpk, dwc)
@@ -376,7 +412,10 @@ def probe_head():
 
 def probe_loss():
     def f():
-        for (Bn, Cn, g, S) in ((2, 17, 14, 224), (1, 17, 32, 512), (2, 1, 28, 224)):
+        # (5, 14: class counts below the kernels' template sizes = the runtime-predicate instantiations; g = 56: patch 4;
+        #  S = 1280: more 4-column groups per row than threads per block in the upsample forward)
+        for (Bn, Cn, g, S) in ((2, 17, 14, 224), (1, 17, 32, 512), (2, 1, 28, 224), (2, 5, 14, 224), (1, 14, 24, 384),
+                               (1, 8, 56, 224), (1, 3, 80, 1280)):
             low = torch.randn(Bn, Cn, g, g, device=dev)
             full = torch.empty(Bn, Cn, S, S, device=dev)
             K.upsample_fwd(low, full)
