@@ -16,6 +16,7 @@
 //   dV += P^T dO,  dK += dS^T Q   (TMEM accumulators over the query loop; P/dS/Q/dO read MN-major in place)
 //   dQ_i = dS K  -> fp32 atomics into dq_accum (one add per key block; converted to bf16 by the caller).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "../../include/vitseg.h"
@@ -531,6 +532,241 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       tmem_ld32(taddr + half * 32, v);
       tmem_ld_wait();
       if (q < N) {
+        // l_tot and the accumulator are both in dropout-scaled units: O = acc * dscale / l_tot, l = l_tot / dscale
+        const float inv = dscale / l_tot;
+        __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH + half * 32;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          u32x8 o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            o.v[k] = pack_bf16(__uint_as_float(v[16 * i + 2 * k]) * inv, __uint_as_float(v[16 * i + 2 * k + 1]) * inv);
+          st_global_256(dst + 16 * i, o);
+        }
+        if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * N + q] = (m2 + log2f(l_tot) - lds) * kLn2;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent form of the short forward: two CTAs per SM loop over (query tile, head, batch) items instead of one CTA
+// per item.  Same phases and the same arithmetic as attn_fwd_short_kernel (bit-identical outputs); what changes is the
+// hand-over between items: barriers and TMEM are set up once, and the Q / K / V loads of the NEXT item are issued as
+// soon as the P·V product of the current one has retired (all of shared memory is dead then), so they travel while
+// the softmax warps read out O and store it.  The one-shot form pays CTA launch, barrier / TMEM set-up and the full
+// TMA latency in front of every item: 1536 CTAs of ~6.5 us for ~2 us of issue-slot work each (r02: 32 % issue utilisation
+// without dropout).  bar_e (256 arrivals) tells the control warp that the O accumulator and the partial-sum exchange of
+// the previous item have been read, i.e. that S of the next item may overwrite the TMEM columns.
+// Item order: a CTA's items are grid-size apart, and the grid is made even, so with a plain decode a CTA would draw the same
+// query tile every time — all full first tiles or all 69-row second tiles at N = 197; the tile index is therefore
+// rotated by the iteration count (CTAs 2k and 2k+1 still cover both tiles of the same (head, batch) in every iteration).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFwdThreads, 2)
+attn_fwd_short_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                              __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int B, int N, int H, float scale,
+                              const DropCfg drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdShortSmem::kBar);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint64_t* bar_e = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * kDH;
+  const int NK = (N + 15) & ~15;
+  const int nq = (N + kBQ - 1) / kBQ;
+  const int total = nq * H * B;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_kv);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_o, 1);
+      mbar_init(bar_e, 256);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- control warp
+    uint8_t* sQ = smem + AttnFwdShortSmem::kQ;
+    uint8_t* sK = smem + AttnFwdShortSmem::kK;
+    uint8_t* sV = smem + AttnFwdShortSmem::kV;
+    const uint32_t aP = smem_u32(smem + AttnFwdShortSmem::kP);
+    auto issue_loads = [&](int w, uint32_t itn) {
+      const int qt = (w % nq + (int)itn) % nq, hb = w / nq, h = hb % H, b = hb / H;
+      mbar_expect_tx(bar_qk, 16384 + NK * 128);
+      tma_load_3d(sQ, &tmap_q, bar_qk, h * kDH, qt * kBQ, b);
+      tma_load_3d(sK, &tmap_kv, bar_qk, D + h * kDH, 0, b);
+      mbar_expect_tx(bar_v, NK * 128);
+      tma_load_3d(sV, &tmap_kv, bar_v, 2 * D + h * kDH, 0, b);
+    };
+    if ((int)blockIdx.x < total && elect_one()) issue_loads(blockIdx.x, 0u);
+    __syncwarp();
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      mbar_wait(bar_qk, ph);
+      if (it > 0) mbar_wait(bar_e, (it - 1) & 1u);   // O and the row sums of the previous item have been read
+      tc_fence_after();
+      if (elect_one()) {   // S = Q K^T : [128 x NK], reduction over head_dim
+        const uint32_t idesc = umma_idesc_bf16(kBQ, NK, 0, 0);
+        const uint64_t ad = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t bd = umma_desc_sw128(smem_u32(sK), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kDH / 16; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, k > 0);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, ph);            // P in smem (over Q / K), S consumed
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      if (elect_one()) {   // O = P V : [128 x 64], reduction over the NK keys, into the (dead) S columns 0-63
+        const uint32_t idesc = umma_idesc_bf16(kBQ, kDH, 0, 1);
+        for (int kk = 0; kk < NK / 16; ++kk) {
+          const uint64_t ad = umma_desc_sw128(aP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(smem_u32(sV) + kk * 2048, 16384, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, kk > 0);
+        }
+        umma_commit(bar_o);
+      }
+      __syncwarp();
+      // P·V has retired: P, Q, K and V are dead — the next item's operands may land while O is read out and stored
+      mbar_wait(bar_o, ph);
+      if (w + (int)gridDim.x < total && elect_one()) issue_loads(w + gridDim.x, it + 1u);
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16);
+    uint8_t* sP = smem + AttnFwdShortSmem::kP;
+    float* s_red = reinterpret_cast<float*>(smem + AttnFwdShortSmem::kRed);
+    const float sl2 = scale * kLog2e;
+    const uint32_t dseed0 = drop.thresh != 0u ? drop_seed(drop) : 0u;
+    const float dscale = drop.thresh != 0u ? drop.scale : 1.0f;
+    const float lds = log2f(dscale);
+    // 16-column chunks [c_beg, c_end) of this thread's row: the two threads of a row split the key axis
+    const int nch = NK >> 4;
+    const int c_beg = half == 0 ? 0 : (nch + 1) >> 1;
+    const int c_end = half == 0 ? (nch + 1) >> 1 : nch;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const int qt = (w % nq + (int)it) % nq, hb = w / nq, h = hb % H, b = hb / H;
+      const int q0 = qt * kBQ;
+      const int q = q0 + r;
+      const bool warp_live = q0 + quad * 32 < N;   // warps whose 32 query rows all lie beyond the sequence only sync
+      const uint32_t dseed = drop.thresh != 0u ? drop_hash((uint32_t)(b * H + h), dseed0) : 0u;
+      const uint32_t drow = (uint32_t)q * (uint32_t)((N + 3) >> 2);
+
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      float m_part = -INFINITY;
+      if (warp_live) {
+        // pass 1: row maximum.  Only the chunk that straddles N needs per-column masking (warp-uniform branch).
+        for (int c = c_beg; c < c_end; c += 2) {
+          uint32_t v0[16], v1[16];
+          const bool two = c + 1 < c_end;
+          tmem_ld16(taddr + c * 16, v0);
+          if (two) tmem_ld16(taddr + c * 16 + 16, v1);
+          tmem_ld_wait();
+          const int lim0 = N - c * 16, lim1 = N - (c + 1) * 16;   // valid columns of each chunk (>= 16: all)
+          if (lim0 >= 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m_part = fmaxf(m_part, __uint_as_float(v0[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < lim0) m_part = fmaxf(m_part, __uint_as_float(v0[i]));
+          }
+          if (two) {
+            if (lim1 >= 16) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) m_part = fmaxf(m_part, __uint_as_float(v1[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < lim1) m_part = fmaxf(m_part, __uint_as_float(v1[i]));
+            }
+          }
+        }
+        s_red[half * 128 + r] = m_part;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // pass 2: p' = exp2(s*c - m) * dscale with the dropout scale folded into the exponent; the row sum is kept in
+      // the same scaled units (the normaliser uses the un-dropped probabilities: dropout acts on the softmax output)
+      float l_part = 0.0f, m2 = 0.0f;
+      if (warp_live) {
+        m2 = fmaxf(m_part, s_red[(half ^ 1) * 128 + r]) * sl2;   // scale > 0: max(s) * c == max(s * c)
+        const float m2s = m2 - lds;
+        for (int c = c_beg; c < c_end; ++c) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c * 16, v);
+          tmem_ld_wait();
+          const int lim = N - c * 16;
+          float pe[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pe[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m2s));
+          if (lim < 16) {   // zero-filled key rows give s = 0, not -inf
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pe[i] = i < lim ? pe[i] : 0.0f;
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            l_part += (pe[i] + pe[i + 1]) + (pe[i + 2] + pe[i + 3]);
+            bool kp[4] = {true, true, true, true};
+            if (drop.thresh != 0u)   // keys 4k .. 4k+3 of a query row share one hash
+              drop_keep4(drow + (uint32_t)((c * 16 + i) >> 2), dseed, drop.thresh, kp);
+            pk[i >> 1] = pack_bf16(kp[0] ? pe[i] : 0.0f, kp[1] ? pe[i + 1] : 0.0f);
+            pk[(i >> 1) + 1] = pack_bf16(kp[2] ? pe[i + 2] : 0.0f, kp[3] ? pe[i + 3] : 0.0f);
+          }
+          uint8_t* tile = sP + (c >> 2) * 16384;
+          const uint32_t slot = uint32_t(c & 3) * 2;
+          *reinterpret_cast<uint4*>(tile + sw128_offset(r, slot)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(tile + sw128_offset(r, slot + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        s_red[(2 + half) * 128 + r] = l_part;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+      float l_tot = 1.0f;
+      uint32_t v[32];
+      if (warp_live) {
+        l_tot = l_part + s_red[(2 + (half ^ 1)) * 128 + r];
+        tmem_ld32(taddr + half * 32, v);
+        tmem_ld_wait();
+      }
+      // the accumulator and the exchanged sums have been read: the next item's S may overwrite them
+      tc_fence_before();
+      mbar_arrive(bar_e);
+      if (warp_live && q < N) {
         // l_tot and the accumulator are both in dropout-scaled units: O = acc * dscale / l_tot, l = l_tot / dscale
         const float inv = dscale / l_tot;
         __nv_bfloat16* dst = ctx + ((size_t)b * N + q) * D + h * kDH + half * 32;
@@ -1432,8 +1668,25 @@ extern "C" int vs_attention_fwd(const void* qkv, void* ctx, float* lse, int32_t 
     }
     DropCfg dcs;
     if (int rc2 = make_drop(&dcs, dropout_p, dropout_seed, dropout_site, (long long)N * (N + 1))) return rc2;
-    dim3 grid_s((N + kBQ - 1) / kBQ, H, B);
-    launch_k(attn_fwd_short_kernel, dim3(grid_s), dim3(kFwdThreads), (size_t)(AttnFwdShortSmem::kTotal), (cudaStream_t)stream, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dcs);
+    // VS_ATTN_FWD_SHORT = persist (default) | oneshot: persistent CTAs looping over the items, or one CTA per item
+    static int persist = -1;
+    if (persist < 0) {
+      const char* e = getenv("VS_ATTN_FWD_SHORT");
+      persist = (e && strcmp(e, "oneshot") == 0) ? 0 : 1;
+      VS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_short_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnFwdShortSmem::kTotal));
+    }
+    const long long items = (long long)((N + kBQ - 1) / kBQ) * H * B;
+    VS_CHECK_ARG(items < (1LL << 31), "vs_attention_fwd: too many (query tile, head, batch) items");
+    if (persist) {
+      const long long slots = 2LL * sm_count();
+      unsigned grid_p = (unsigned)(items < slots ? items : slots);
+      if (grid_p > 1u) grid_p &= ~1u;   // even: the tile rotation pairs CTAs 2k / 2k+1 (an odd item count only occurs for nq = 1)
+      launch_k(attn_fwd_short_persist_kernel, dim3(grid_p), dim3(kFwdThreads), (size_t)(AttnFwdShortSmem::kTotal), (cudaStream_t)stream, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dcs);
+    } else {
+      dim3 grid_s((N + kBQ - 1) / kBQ, H, B);
+      launch_k(attn_fwd_short_kernel, dim3(grid_s), dim3(kFwdThreads), (size_t)(AttnFwdShortSmem::kTotal), (cudaStream_t)stream, tm, tkv, (__nv_bfloat16*)ctx, lse, B, N, H, scale, dcs);
+    }
     VS_CHECK_LAUNCH();
     return 0;
   }
