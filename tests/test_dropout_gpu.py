@@ -261,3 +261,37 @@ def test_attention_dropout_index_space_is_independent_of_the_batch():
     nodrop = torch.empty_like(ctx1)
     K.attention_fwd(qkv[:1].contiguous(), nodrop, lse1, 1, N, H, 0.125)
     assert not torch.equal(nodrop, ctx1)
+
+
+def test_attention_mask_matches_the_numpy_restatement_of_the_generator():
+    """The attention-probability mask (four decisions per hash, drop_keep4 in csrc/common.cuh) bit for bit against
+    tools/dropout_quality.py's numpy restatement — the offline quality numbers quoted in DESIGN.md are about THIS generator."""
+    import os
+    import sys
+
+    import numpy as np
+
+    from visiontransformer_b200 import kernels as K
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from dropout_quality import quad_fields
+
+    def h3(x, seed):   # drop_hash
+        x = (int(x) ^ int(seed)) & 0xFFFFFFFF
+        x = (x * 0x9E3779B1) & 0xFFFFFFFF; x ^= x >> 16
+        x = (x * 0x85EBCA6B) & 0xFFFFFFFF; x ^= x >> 13
+        x = (x * 0xC2B2AE35) & 0xFFFFFFFF; x ^= x >> 16
+        return x
+
+    dev = _dev()
+    step, site, p, N, BH = 4321, 1003, 0.1, 37, 3
+    seed = torch.tensor([step], device=dev, dtype=torch.int32)
+    got = K.dropout_mask(torch.empty(BH * N * N, device=dev, dtype=torch.uint8), 1, (p, seed, site), N).cpu().numpy()
+    thresh = int(p * 65536.0 + 0.5)
+    sd = h3((site + 0x27D4EB2F) & 0xFFFFFFFF, h3(step, 0x9E3779B9))            # drop_seed(step, site)
+    exp = np.empty((BH, N, N), dtype=np.uint8)
+    nquad = (N + 3) >> 2
+    for bh in range(BH):
+        quads = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(nquad) + np.arange(nquad, dtype=np.uint64)[None, :])
+        f = quad_fields(quads.reshape(-1), h3(bh, sd)).reshape(N, nquad * 4)   # [query, key] uniforms
+        exp[bh] = (f[:, :N] >= thresh)
+    assert np.array_equal(got.reshape(BH, N, N), exp)
